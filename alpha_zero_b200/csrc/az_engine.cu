@@ -1,0 +1,684 @@
+// az_engine.cu — host side of the C ABI declared in include/az_engine.h.
+//
+// Owns the device buffers (structure-of-arrays state of every game slot, az_state.h), builds the
+// selection tables, validates arguments the way the reference's Python does, and launches the
+// warp-per-game kernels of az_kernels.cuh and the network kernels of az_net*.cu on one stream.
+// There is no CPU fallback: without a CUDA device az_create fails.
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "az_kernels.cuh"
+#include "az_net.h"
+
+thread_local std::string g_az_error;
+
+struct az_engine {
+  az_config cfg;
+  AzRt rt;
+  AzState E;
+  std::vector<void*> allocs;
+  AzNet* net = nullptr;
+  // staging
+  int32_t *d_slots = nullptr, *d_aux = nullptr, *d_out = nullptr;
+  float* d_fout = nullptr;
+  double* d_dout = nullptr;
+  int8_t* d_stage_obs = nullptr;
+  float *d_stage_pri = nullptr, *d_stage_val = nullptr;
+  double *d_pbc_fresh = nullptr, *d_pbc_f32 = nullptr, *d_sqrt = nullptr;
+  double tab_cb = -1, tab_ci = -1;
+  std::vector<int32_t> active;  // slots of the current split-phase search, ascending
+  int last_total = 0;
+  bool selfplay = false;
+  unsigned long long drained_games = 0;
+  float last_net_ms = 0.f;
+  int last_net_evals = 0;
+#ifndef AZ_EMU
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+#endif
+};
+
+template <class T>
+static T* dev_alloc(az_engine* e, size_t count) {
+  void* p = rt_alloc(count * sizeof(T));
+  if (p) e->allocs.push_back(p);
+  return (T*)p;
+}
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+extern "C" const char* az_last_error(void) { return g_az_error.c_str(); }
+extern "C" int az_version(void) { return 100; }
+
+static void build_tables(az_engine* e, double cb, double ci) {
+  if (cb == e->tab_cb && ci == e->tab_ci) return;
+  const int n = e->E.d.table_len;
+  std::vector<double> fresh(n), f32(n), sq(n);
+  for (int i = 0; i < n; ++i) {
+    // fresh root: N is a Python float -> double arithmetic (mcts_v2.py:56-62,101)
+    fresh[i] = log((1.0 + (double)i + cb) / cb) + ci;
+    // np.float32 N: 1 + N, + c_base, / c_base all round to float32 before math.log (numpy>=2 scalar rules)
+    volatile float s = 1.0f + (float)i;
+    s = s + (float)cb;
+    s = s / (float)cb;
+    f32[i] = log((double)s) + ci;
+    sq[i] = sqrt((double)i);
+  }
+  rt_h2d(e->rt, e->d_pbc_fresh, fresh.data(), n * sizeof(double));
+  rt_h2d(e->rt, e->d_pbc_f32, f32.data(), n * sizeof(double));
+  rt_h2d(e->rt, e->d_sqrt, sq.data(), n * sizeof(double));
+  e->tab_cb = cb;
+  e->tab_ci = ci;
+}
+
+extern "C" int az_create(const az_config* cfg, az_engine** out) {
+  if (!cfg || !out) return az_fail(AZ_ERR_BAD_ARG, "az_create: null argument");
+  if (cfg->game != AZ_GAME_GO && cfg->game != AZ_GAME_GOMOKU) return az_fail(AZ_ERR_BAD_ARG, "az_create: unknown game");
+  if (cfg->board_size < 3 || cfg->board_size > 19) return az_fail(AZ_ERR_BAD_ARG, "az_create: board_size must be in [3, 19]");
+  if (cfg->num_stack < 1 || cfg->num_stack > 8) return az_fail(AZ_ERR_BAD_ARG, "az_create: num_stack must be in [1, 8]");
+  if (cfg->num_games < 1) return az_fail(AZ_ERR_BAD_ARG, "az_create: num_games must be positive");
+  if (cfg->max_simulations < 1 || cfg->max_parallel < 1) return az_fail(AZ_ERR_BAD_ARG, "az_create: max_simulations / max_parallel must be positive");
+  az_engine* e = new az_engine();
+  e->cfg = *cfg;
+  int rc = rt_init(e->rt, cfg->device);
+  if (rc) { delete e; return rc; }
+  AzDims& d = e->E.d;
+  d.game = cfg->game;
+  d.n = cfg->board_size;
+  d.nc = d.n * d.n;
+  d.ncp = round_up(d.nc, 32);
+  d.A = d.nc + (cfg->game == AZ_GAME_GO ? 1 : 0);
+  d.Ap = round_up(d.A, 32);
+  d.num_stack = cfg->num_stack;
+  d.planes = 2 * cfg->num_stack + 1;
+  d.obs_bytes = d.planes * d.nc;
+  d.max_steps = cfg->max_steps > 0 ? cfg->max_steps : 2 * d.nc;
+  d.num_to_win = cfg->num_to_win > 0 ? cfg->num_to_win : 5;
+  d.komi = cfg->komi;
+  d.G = cfg->num_games;
+  d.Pmax = cfg->max_parallel;
+  d.cap = cfg->max_simulations + 6 * cfg->max_parallel + 16;
+  if (d.cap > 32000) { delete e; return az_fail(AZ_ERR_CAPACITY, "az_create: node pool exceeds int16 child links"); }
+  d.pass_move = cfg->game == AZ_GAME_GO ? d.nc : -1;
+  d.table_len = d.cap + 64;
+  d.max_len = (cfg->game == AZ_GAME_GO ? d.max_steps : d.nc) + 1;
+  d.ring_cap = cfg->sample_ring > 0 ? cfg->sample_ring : std::max(4 * d.max_len, 2 * d.G * 8);
+  e->cfg.max_steps = d.max_steps;
+  e->cfg.sample_ring = d.ring_cap;
+  AzState& E = e->E;
+  const size_t G = d.G, nodes = G * 2 * d.cap, rows = G * d.Pmax;
+  E.board = dev_alloc<int8_t>(e, G * d.ncp);
+  E.hist = dev_alloc<int8_t>(e, G * 8 * d.ncp);
+  E.env_i = dev_alloc<int32_t>(e, G * ENV_INTS);
+  E.root_legal = dev_alloc<uint8_t>(e, G * d.Ap);
+  E.cN = dev_alloc<float>(e, nodes * d.Ap);
+  E.cW = dev_alloc<float>(e, nodes * d.Ap);
+  E.cP = dev_alloc<float>(e, nodes * d.Ap);
+  E.cidx = dev_alloc<int16_t>(e, nodes * d.Ap);
+  E.parent = dev_alloc<int16_t>(e, nodes);
+  E.pmove = dev_alloc<int16_t>(e, nodes);
+  E.nvloss = dev_alloc<int16_t>(e, nodes);
+  E.nto_play = dev_alloc<int8_t>(e, nodes);
+  E.expanded = dev_alloc<uint8_t>(e, nodes);
+  E.tree_i = dev_alloc<int32_t>(e, G * TREE_INTS);
+  E.root_nw = dev_alloc<double>(e, G * 2);
+  E.root_p64 = dev_alloc<double>(e, G * d.Ap);
+  E.noise = dev_alloc<double>(e, G * d.Ap);
+  E.remap = dev_alloc<int16_t>(e, G * d.cap);
+  e->d_pbc_fresh = dev_alloc<double>(e, d.table_len);
+  e->d_pbc_f32 = dev_alloc<double>(e, d.table_len);
+  e->d_sqrt = dev_alloc<double>(e, d.table_len);
+  E.pbc_fresh = e->d_pbc_fresh;
+  E.pbc_f32 = e->d_pbc_f32;
+  E.sqrt_tab = e->d_sqrt;
+  E.leaf_node = dev_alloc<int16_t>(e, rows);
+  E.leaf_obs = dev_alloc<int8_t>(e, rows * d.obs_bytes);
+  E.priors = dev_alloc<float>(e, rows * d.Ap);
+  E.values = dev_alloc<float>(e, rows);
+  E.leaf_rows = dev_alloc<int32_t>(e, rows);
+  E.leaf_total = dev_alloc<int32_t>(e, 4);
+  E.leaf_count = dev_alloc<int32_t>(e, G);
+  E.res_pi = dev_alloc<double>(e, G * d.Ap);
+  E.res_q = dev_alloc<double>(e, G * 2);
+  E.res_move = dev_alloc<int32_t>(e, G);
+  E.g_obs = dev_alloc<int8_t>(e, G * d.max_len * d.obs_bytes);
+  E.g_pi = dev_alloc<float>(e, G * d.max_len * d.A);
+  E.g_to_play = dev_alloc<int8_t>(e, G * d.max_len);
+  E.r_obs = dev_alloc<int8_t>(e, (size_t)d.ring_cap * d.obs_bytes);
+  E.r_pi = dev_alloc<float>(e, (size_t)d.ring_cap * d.A);
+  E.r_z = dev_alloc<float>(e, d.ring_cap);
+  E.games_ring = dev_alloc<int32_t>(e, (size_t)AZ_GAMES_RING * GR_INTS);
+  E.counters = dev_alloc<unsigned long long>(e, CT_COUNT);
+  e->d_slots = dev_alloc<int32_t>(e, G);
+  e->d_aux = dev_alloc<int32_t>(e, G);
+  e->d_out = dev_alloc<int32_t>(e, G * 3);
+  e->d_fout = dev_alloc<float>(e, 16);
+  e->d_dout = dev_alloc<double>(e, 16);
+  e->d_stage_obs = dev_alloc<int8_t>(e, rows * d.obs_bytes);
+  e->d_stage_pri = dev_alloc<float>(e, rows * d.A);
+  e->d_stage_val = dev_alloc<float>(e, rows);
+  if (!E.counters || !e->d_stage_val || !E.cidx || !E.g_obs) {
+    az_destroy(e);
+    return az_fail(AZ_ERR_CUDA, "az_create: device allocation failed");
+  }
+  memset(&E.s, 0, sizeof(E.s));
+  E.s.seed = cfg->seed;
+  if (cfg->num_filters > 0) {
+    std::string err;
+    e->net = aznet_create(d, e->cfg, e->rt, (int)rows, err);
+    if (!e->net) { az_destroy(e); return az_fail(AZ_ERR_CUDA, "az_create: network: " + err); }
+  }
+#ifndef AZ_EMU
+  cudaEventCreate(&e->ev0);
+  cudaEventCreate(&e->ev1);
+#endif
+  // every slot starts as a freshly reset game
+  std::vector<int32_t> all(G);
+  for (size_t i = 0; i < G; ++i) all[i] = (int32_t)i;
+  rt_h2d(e->rt, e->d_slots, all.data(), G * sizeof(int32_t));
+  AZ_LAUNCH_WARPS(e->rt, k_env_reset, (int)G, d, E, e->d_slots);
+  rc = rt_sync(e->rt);
+  if (rc) { az_destroy(e); return rc; }
+  *out = e;
+  return AZ_OK;
+}
+
+extern "C" int az_destroy(az_engine* e) {
+  if (!e) return AZ_OK;
+  rt_sync(e->rt);
+  if (e->net) aznet_destroy(e->net);
+  for (void* p : e->allocs) rt_free(p);
+#ifndef AZ_EMU
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+#endif
+  rt_destroy(e->rt);
+  delete e;
+  return AZ_OK;
+}
+
+extern "C" int az_get_config(az_engine* e, az_config* out) {
+  if (!e || !out) return az_fail(AZ_ERR_BAD_ARG, "null argument");
+  *out = e->cfg;
+  return AZ_OK;
+}
+extern "C" int az_num_actions(az_engine* e) { return e ? e->E.d.A : AZ_ERR_BAD_ARG; }
+extern "C" int az_obs_bytes(az_engine* e) { return e ? e->E.d.obs_bytes : AZ_ERR_BAD_ARG; }
+
+static int check_slot(az_engine* e, int slot) {
+  if (!e) return az_fail(AZ_ERR_BAD_ARG, "null engine");
+  if (slot < 0 || slot >= e->E.d.G) return az_fail(AZ_ERR_BAD_ARG, "slot out of range");
+  return AZ_OK;
+}
+
+static int upload_slots(az_engine* e, const int32_t* slots, int n) {
+  if (!e || !slots || n < 1 || n > e->E.d.G) return az_fail(AZ_ERR_BAD_ARG, "bad slot list");
+  for (int i = 0; i < n; ++i)
+    if (slots[i] < 0 || slots[i] >= e->E.d.G) return az_fail(AZ_ERR_BAD_ARG, "slot out of range");
+  rt_h2d(e->rt, e->d_slots, slots, n * sizeof(int32_t));
+  return AZ_OK;
+}
+
+// ---- weights / network ---------------------------------------------------------------------------
+extern "C" int az_set_weights(az_engine* e, const float* const* tensors, const int64_t* numel, int32_t n_tensors) {
+  if (!e || !tensors || !numel) return az_fail(AZ_ERR_BAD_ARG, "null argument");
+  if (!e->net) return az_fail(AZ_ERR_STATE, "engine was created without a network (num_filters == 0)");
+  std::string err;
+  int rc = aznet_set_weights(e->net, e->rt, tensors, numel, n_tensors, err);
+  if (rc) return az_fail(rc, "az_set_weights: " + err);
+  return rt_sync(e->rt);
+}
+
+extern "C" int az_net_forward(az_engine* e, const int8_t* obs, int32_t n, float* priors, float* values) {
+  if (!e || !obs || !priors || !values) return az_fail(AZ_ERR_BAD_ARG, "null argument");
+  if (!e->net || !aznet_ready(e->net)) return az_fail(AZ_ERR_STATE, "network weights not set");
+  const AzDims& d = e->E.d;
+  const int cap = d.G * d.Pmax;
+  for (int off = 0; off < n; off += cap) {
+    const int m = std::min(cap, n - off);
+    rt_h2d(e->rt, e->d_stage_obs, obs + (size_t)off * d.obs_bytes, (size_t)m * d.obs_bytes);
+    int32_t cnt = m;
+    rt_h2d(e->rt, e->E.leaf_total + 2, &cnt, sizeof(cnt));
+    int rc = aznet_forward(e->net, e->rt, e->d_stage_obs, nullptr, e->E.leaf_total + 2, m, e->E.priors, e->E.values, d.Ap);
+    if (rc) return az_fail(rc, "az_net_forward failed");
+    std::vector<float> tmp((size_t)m * d.Ap);
+    rt_d2h(e->rt, tmp.data(), e->E.priors, tmp.size() * sizeof(float));
+    for (int i = 0; i < m; ++i) memcpy(priors + (size_t)(off + i) * d.A, tmp.data() + (size_t)i * d.Ap, d.A * sizeof(float));
+    rt_d2h(e->rt, values + off, e->E.values, m * sizeof(float));
+  }
+  return rt_sync(e->rt);
+}
+
+// ---- BoardGameEnv ----------------------------------------------------------------------------------
+extern "C" int az_env_reset(az_engine* e, const int32_t* slots, int32_t n) {
+  int rc = upload_slots(e, slots, n);
+  if (rc) return rc;
+  AZ_LAUNCH_WARPS(e->rt, k_env_reset, n, e->E.d, e->E, e->d_slots);
+  return rt_sync(e->rt);
+}
+
+extern "C" int az_env_step(az_engine* e, const int32_t* slots, const int32_t* actions, int32_t n, float* rewards, int32_t* dones) {
+  int rc = upload_slots(e, slots, n);
+  if (rc) return rc;
+  if (!actions) return az_fail(AZ_ERR_BAD_ARG, "null actions");
+  rt_h2d(e->rt, e->d_aux, actions, n * sizeof(int32_t));
+  AZ_LAUNCH_WARPS(e->rt, k_env_step, n, e->E.d, e->E, e->d_slots, e->d_aux, e->d_out);
+  std::vector<int32_t> out(n * 3);
+  rt_d2h(e->rt, out.data(), e->d_out, out.size() * sizeof(int32_t));
+  rc = rt_sync(e->rt);
+  if (rc) return rc;
+  int first_err = 0, err_i = -1;
+  for (int i = 0; i < n; ++i) {
+    if (rewards) rewards[i] = 0.5f * (float)out[i * 3 + 1];
+    if (dones) dones[i] = out[i * 3 + 2];
+    if (out[i * 3] && !first_err) { first_err = out[i * 3]; err_i = i; }
+  }
+  if (first_err == AZ_ERR_GAME_OVER) return az_fail(first_err, "Game is over, call reset before using step method.");
+  if (first_err == AZ_ERR_INVALID_ACTION) return az_fail(first_err, "Invalid action. The action " + std::to_string(actions[err_i]) + " is out of bound.");
+  if (first_err == AZ_ERR_ILLEGAL_ACTION) return az_fail(first_err, "Illegal action " + std::to_string(actions[err_i]) + ".");
+  return AZ_OK;
+}
+
+extern "C" int az_env_observation(az_engine* e, int32_t slot, int8_t* out) {
+  int rc = check_slot(e, slot);
+  if (rc) return rc;
+  AZ_LAUNCH_WARPS(e->rt, k_env_obs, 1, e->E.d, e->E, slot, e->d_stage_obs);
+  rt_d2h(e->rt, out, e->d_stage_obs, e->E.d.obs_bytes);
+  return rt_sync(e->rt);
+}
+
+extern "C" int az_env_legal_actions(az_engine* e, int32_t slot, uint8_t* out) {
+  int rc = check_slot(e, slot);
+  if (rc) return rc;
+  rt_d2h(e->rt, out, e->E.root_legal + (size_t)slot * e->E.d.Ap, e->E.d.A);
+  return AZ_OK;
+}
+
+extern "C" int az_env_board(az_engine* e, int32_t slot, int8_t* out) {
+  int rc = check_slot(e, slot);
+  if (rc) return rc;
+  const AzDims& d = e->E.d;
+  rt_d2h(e->rt, out, e->E.board + (size_t)slot * d.ncp, d.nc);
+  if (d.game == AZ_GAME_GOMOKU)
+    for (int i = 0; i < d.nc; ++i)
+      if (out[i] == -1) out[i] = 2;  // reference ids (envs/base.py:33-34)
+  return AZ_OK;
+}
+
+static int ext_player(const AzDims& d, int v) { return (d.game == AZ_GAME_GOMOKU && v == -1) ? 2 : v; }
+
+extern "C" int az_env_scalars(az_engine* e, int32_t slot, int32_t* out) {
+  int rc = check_slot(e, slot);
+  if (rc) return rc;
+  int32_t ei[ENV_INTS];
+  rt_d2h(e->rt, ei, e->E.env_i + (size_t)slot * ENV_INTS, sizeof(ei));
+  const AzDims& d = e->E.d;
+  out[0] = ext_player(d, ei[EI_TO_PLAY]);
+  out[1] = ei[EI_STEPS];
+  out[2] = ei[EI_LAST_MOVE];
+  out[3] = ext_player(d, ei[EI_LAST_PLAYER]);
+  out[4] = ext_player(d, ei[EI_WINNER]);
+  out[5] = ei[EI_DONE];
+  out[6] = ei[EI_KO];
+  out[7] = ei[EI_BY_RESIGN];
+  out[8] = ei[EI_CAPS_B];
+  out[9] = ei[EI_CAPS_W];
+  out[10] = ei[EI_NUM_PASSES];
+  return AZ_OK;
+}
+
+extern "C" int az_env_score(az_engine* e, int32_t slot, float* out_score) {
+  int rc = check_slot(e, slot);
+  if (rc) return rc;
+  AZ_LAUNCH_WARPS(e->rt, k_env_score, 1, e->E.d, e->E, slot, e->d_fout);
+  rt_d2h(e->rt, out_score, e->d_fout, sizeof(float));
+  return rt_sync(e->rt);
+}
+
+extern "C" int az_env_copy(az_engine* e, int32_t src, int32_t dst) {
+  int rc = check_slot(e, src);
+  if (!rc) rc = check_slot(e, dst);
+  if (rc) return rc;
+  if (src == dst) return AZ_OK;
+  AZ_LAUNCH_WARPS(e->rt, k_env_copy, 1, e->E.d, e->E, src, dst);
+  return rt_sync(e->rt);
+}
+
+extern "C" int az_env_state_bytes(az_engine* e) {
+  if (!e) return AZ_ERR_BAD_ARG;
+  const AzDims& d = e->E.d;
+  return d.ncp * 9 + ENV_INTS * 4 + d.Ap;
+}
+
+extern "C" int az_env_export(az_engine* e, int32_t slot, uint8_t* out) {
+  int rc = check_slot(e, slot);
+  if (rc) return rc;
+  const AzDims& d = e->E.d;
+  rt_d2h(e->rt, out, e->E.board + (size_t)slot * d.ncp, d.ncp);
+  rt_d2h(e->rt, out + d.ncp, e->E.hist + (size_t)slot * 8 * d.ncp, 8 * d.ncp);
+  rt_d2h(e->rt, out + 9 * d.ncp, e->E.env_i + (size_t)slot * ENV_INTS, ENV_INTS * 4);
+  rt_d2h(e->rt, out + 9 * d.ncp + ENV_INTS * 4, e->E.root_legal + (size_t)slot * d.Ap, d.Ap);
+  return AZ_OK;
+}
+
+extern "C" int az_env_import(az_engine* e, int32_t slot, const uint8_t* in) {
+  int rc = check_slot(e, slot);
+  if (rc) return rc;
+  const AzDims& d = e->E.d;
+  rt_h2d(e->rt, e->E.board + (size_t)slot * d.ncp, in, d.ncp);
+  rt_h2d(e->rt, e->E.hist + (size_t)slot * 8 * d.ncp, in + d.ncp, 8 * d.ncp);
+  rt_h2d(e->rt, e->E.env_i + (size_t)slot * ENV_INTS, in + 9 * d.ncp, ENV_INTS * 4);
+  rt_h2d(e->rt, e->E.root_legal + (size_t)slot * d.Ap, in + 9 * d.ncp + ENV_INTS * 4, d.Ap);
+  int32_t ti[TREE_INTS] = {0};
+  rt_h2d(e->rt, e->E.tree_i + (size_t)slot * TREE_INTS, ti, sizeof(ti));
+  return AZ_OK;
+}
+
+// ---- search ------------------------------------------------------------------------------------------
+static int set_search_cfg(az_engine* e, const az_search_params* p) {
+  if (!p) return az_fail(AZ_ERR_BAD_ARG, "null search params");
+  if (p->num_simulations < 1) return az_fail(AZ_ERR_BAD_ARG, "Expect `num_simulations` to a positive integer, got " + std::to_string(p->num_simulations));
+  const int P = p->num_parallel > 1 ? p->num_parallel : 1;
+  const AzDims& d = e->E.d;
+  if (P > d.Pmax) return az_fail(AZ_ERR_CAPACITY, "num_parallel exceeds the engine's max_parallel");
+  AzSearchCfg& s = e->E.s;
+  s.P = P;
+  s.use_vloss = P > 1;
+  s.tries = P > 1 ? 2 * P : 1;
+  s.sims_bound = p->num_simulations + (P > 1 ? P : 0);
+  if (s.sims_bound + 4 * P + 16 > d.cap) return az_fail(AZ_ERR_CAPACITY, "num_simulations exceeds the engine's node pool (max_simulations)");
+  s.root_noise = p->root_noise;
+  s.deterministic = p->deterministic;
+  build_tables(e, p->c_puct_base, p->c_puct_init);
+  return AZ_OK;
+}
+
+extern "C" int az_search_begin(az_engine* e, const int32_t* slots, const int32_t* reuse, int32_t n, const az_search_params* p,
+                               int32_t warm_up, const double* noise) {
+  if (!e) return az_fail(AZ_ERR_BAD_ARG, "null engine");
+  int rc = set_search_cfg(e, p);
+  if (rc) return rc;
+  for (int i = 1; i < n; ++i)
+    if (slots[i] <= slots[i - 1]) return az_fail(AZ_ERR_BAD_ARG, "az_search_begin: slots must be strictly ascending");
+  rc = upload_slots(e, slots, n);
+  if (rc) return rc;
+  const AzDims& d = e->E.d;
+  // RuntimeError('Game is over.') (mcts_v2.py:360)
+  for (int i = 0; i < n; ++i) {
+    int32_t done = 0;
+    rt_d2h(e->rt, &done, e->E.env_i + (size_t)slots[i] * ENV_INTS + EI_DONE, sizeof(done));
+    if (done) return az_fail(AZ_ERR_GAME_OVER, "Game is over.");
+  }
+  e->E.s.selfplay = 0;
+  e->selfplay = false;
+  e->E.s.host_noise = (p->root_noise && noise) ? 1 : 0;
+  if (e->E.s.host_noise) {
+    std::vector<double> tmp((size_t)d.Ap, 0.0);
+    for (int i = 0; i < n; ++i) {
+      std::copy(noise + (size_t)i * d.A, noise + (size_t)(i + 1) * d.A, tmp.begin());
+      rt_h2d(e->rt, e->E.noise + (size_t)slots[i] * d.Ap, tmp.data(), d.Ap * sizeof(double));
+    }
+  }
+  std::vector<int32_t> ru(n, 0);
+  if (reuse) ru.assign(reuse, reuse + n);
+  rt_h2d(e->rt, e->d_aux, ru.data(), n * sizeof(int32_t));
+  AZ_LAUNCH_THREADS(e->rt, k_clear_active, d.G, e->E);
+  AZ_LAUNCH_WARPS(e->rt, k_search_begin, n, d, e->E, e->d_slots, e->d_aux, warm_up ? 1 : 0);
+  e->active.assign(slots, slots + n);
+  e->last_total = 0;
+  return rt_sync(e->rt);
+}
+
+static int collect_and_compact(az_engine* e, int32_t tot[2]) {
+  const AzDims& d = e->E.d;
+  AZ_LAUNCH_WARPS(e->rt, k_collect, d.G, d, e->E);
+#ifdef AZ_EMU
+  e->rt.launches++;
+  k_compact(e->E, d.G);
+#else
+  e->rt.launches++;
+  k_compact<<<1, 1024, 0, e->rt.stream>>>(e->E, d.G);
+#endif
+  rt_d2h(e->rt, tot, e->E.leaf_total, 2 * sizeof(int32_t));
+  return rt_sync(e->rt);
+}
+
+extern "C" int az_search_select(az_engine* e, int8_t* leaf_obs, int32_t* counts, int32_t* n_leaves, int32_t* n_active) {
+  if (!e || !n_leaves || !n_active) return az_fail(AZ_ERR_BAD_ARG, "null argument");
+  if (e->active.empty()) return az_fail(AZ_ERR_STATE, "az_search_select: no search in progress");
+  const AzDims& d = e->E.d;
+  int32_t tot[2] = {0, 0};
+  int rc = collect_and_compact(e, tot);
+  if (rc) return rc;
+  e->last_total = tot[0];
+  *n_leaves = tot[0];
+  *n_active = tot[1];
+  if (tot[0] > 0 && leaf_obs) {
+    AZ_LAUNCH_THREADS(e->rt, k_gather_obs, (long long)tot[0] * d.obs_bytes, e->E, e->d_stage_obs);
+    rt_d2h(e->rt, leaf_obs, e->d_stage_obs, (size_t)tot[0] * d.obs_bytes);
+  }
+  if (counts) {
+    std::vector<int32_t> all(d.G);
+    rt_d2h(e->rt, all.data(), e->E.leaf_count, d.G * sizeof(int32_t));
+    for (size_t i = 0; i < e->active.size(); ++i) counts[i] = all[e->active[i]];
+  }
+  return rt_sync(e->rt);
+}
+
+extern "C" int az_search_apply(az_engine* e, const float* priors, const float* values, int32_t n_leaves) {
+  if (!e) return az_fail(AZ_ERR_BAD_ARG, "null engine");
+  if (n_leaves != e->last_total) return az_fail(AZ_ERR_BAD_ARG, "az_search_apply: leaf count does not match the last select");
+  const AzDims& d = e->E.d;
+  if (n_leaves > 0) {
+    if (!priors || !values) return az_fail(AZ_ERR_BAD_ARG, "null priors / values");
+    rt_h2d(e->rt, e->d_stage_pri, priors, (size_t)n_leaves * d.A * sizeof(float));
+    rt_h2d(e->rt, e->d_stage_val, values, (size_t)n_leaves * sizeof(float));
+    AZ_LAUNCH_THREADS(e->rt, k_scatter_eval, (long long)n_leaves * d.A, e->E, e->d_stage_pri, e->d_stage_val);
+  }
+  AZ_LAUNCH_WARPS(e->rt, k_apply, d.G, d, e->E);
+  e->last_total = 0;
+  return rt_sync(e->rt);
+}
+
+extern "C" int az_search_run(az_engine* e) {
+  if (!e) return az_fail(AZ_ERR_BAD_ARG, "null engine");
+  if (!e->net || !aznet_ready(e->net)) return az_fail(AZ_ERR_STATE, "az_search_run: network weights not set");
+  const AzDims& d = e->E.d;
+  for (int it = 0; it < 1000000; ++it) {
+    int32_t tot[2];
+    int rc = collect_and_compact(e, tot);
+    if (rc) return rc;
+    if (tot[1] == 0) break;
+    if (tot[0] > 0) {
+      rc = aznet_forward(e->net, e->rt, e->E.leaf_obs, e->E.leaf_rows, e->E.leaf_total, d.G * d.Pmax, e->E.priors, e->E.values, d.Ap);
+      if (rc) return az_fail(rc, "network forward failed");
+    }
+    AZ_LAUNCH_WARPS(e->rt, k_apply, d.G, d, e->E);
+  }
+  return rt_sync(e->rt);
+}
+
+extern "C" int az_search_result(az_engine* e, int32_t slot, float* child_N, float* child_W, double* pi, double* root_q,
+                                int32_t* argmax_move) {
+  int rc = check_slot(e, slot);
+  if (rc) return rc;
+  const AzDims& d = e->E.d;
+  int32_t ti[TREE_INTS];
+  rt_d2h(e->rt, ti, e->E.tree_i + (size_t)slot * TREE_INTS, sizeof(ti));
+  if (ti[TI_STATE] != ST_DONE) return az_fail(AZ_ERR_STATE, "az_search_result: search not finished");
+  const size_t row0 = ((size_t)slot * 2 + ti[TI_BUF]) * d.cap * d.Ap;
+  if (child_N) rt_d2h(e->rt, child_N, e->E.cN + row0, d.A * sizeof(float));
+  if (child_W) rt_d2h(e->rt, child_W, e->E.cW + row0, d.A * sizeof(float));
+  if (pi) rt_d2h(e->rt, pi, e->E.res_pi + (size_t)slot * d.Ap, d.A * sizeof(double));
+  if (root_q) rt_d2h(e->rt, root_q, e->E.res_q + (size_t)slot * 2, sizeof(double));
+  if (argmax_move) rt_d2h(e->rt, argmax_move, e->E.res_move + slot, sizeof(int32_t));
+  return AZ_OK;
+}
+
+extern "C" int az_search_commit(az_engine* e, int32_t slot, int32_t move, double* best_child_q, int32_t* has_next) {
+  int rc = check_slot(e, slot);
+  if (rc) return rc;
+  if (move < 0 || move >= e->E.d.A) return az_fail(AZ_ERR_BAD_ARG, "az_search_commit: move out of range");
+  AZ_LAUNCH_WARPS(e->rt, k_commit, 1, e->E.d, e->E, slot, move, e->d_dout);
+  double out[2];
+  rt_d2h(e->rt, out, e->d_dout, sizeof(out));
+  if (best_child_q) *best_child_q = out[0];
+  if (has_next) *has_next = (int32_t)out[1];
+  return rt_sync(e->rt);
+}
+
+// ---- device-resident self-play -------------------------------------------------------------------------
+extern "C" int az_selfplay_begin(az_engine* e, const az_selfplay_params* p) {
+  if (!e || !p) return az_fail(AZ_ERR_BAD_ARG, "null argument");
+  if (!e->net || !aznet_ready(e->net)) return az_fail(AZ_ERR_STATE, "az_selfplay_begin: network weights not set");
+  int rc = set_search_cfg(e, &p->search);
+  if (rc) return rc;
+  AzSearchCfg& s = e->E.s;
+  s.selfplay = 1;
+  s.host_noise = 0;
+  s.warm_up_steps = p->warm_up_steps;
+  s.check_resign_after = p->check_resign_after_steps;
+  s.resign_threshold = p->resign_threshold;
+  s.disable_resign_ratio = p->disable_resign_ratio;
+  e->selfplay = true;
+  e->active.clear();
+  rt_zero(e->rt, e->E.counters, CT_COUNT * sizeof(unsigned long long));
+  e->drained_games = 0;
+  AZ_LAUNCH_WARPS(e->rt, k_selfplay_begin, e->E.d.G, e->E.d, e->E);
+  return rt_sync(e->rt);
+}
+
+extern "C" int az_selfplay_tick(az_engine* e, int32_t n_ticks) {
+  if (!e) return az_fail(AZ_ERR_BAD_ARG, "null engine");
+  if (!e->selfplay) return az_fail(AZ_ERR_STATE, "az_selfplay_tick: call az_selfplay_begin first");
+  const AzDims& d = e->E.d;
+  for (int t = 0; t < n_ticks; ++t) {
+    AZ_LAUNCH_WARPS(e->rt, k_collect, d.G, d, e->E);
+#ifndef AZ_EMU
+    e->rt.launches++;
+    k_compact<<<1, 1024, 0, e->rt.stream>>>(e->E, d.G);
+    if (t == n_ticks - 1) cudaEventRecord(e->ev0, e->rt.stream);
+#else
+    k_compact(e->E, d.G);
+#endif
+    int rc = aznet_forward(e->net, e->rt, e->E.leaf_obs, e->E.leaf_rows, e->E.leaf_total, d.G * d.Pmax, e->E.priors, e->E.values, d.Ap);
+    if (rc) return az_fail(rc, "network forward failed");
+#ifndef AZ_EMU
+    if (t == n_ticks - 1) cudaEventRecord(e->ev1, e->rt.stream);
+#endif
+    AZ_LAUNCH_WARPS(e->rt, k_apply, d.G, d, e->E);
+    AZ_LAUNCH_WARPS(e->rt, k_advance, d.G, d, e->E);
+  }
+#ifndef AZ_EMU
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return az_fail(AZ_ERR_CUDA, std::string("CUDA launch error: ") + cudaGetErrorString(ce));
+#endif
+  return AZ_OK;
+}
+
+extern "C" int az_sync(az_engine* e) { return e ? rt_sync(e->rt) : az_fail(AZ_ERR_BAD_ARG, "null engine"); }
+
+extern "C" int az_get_counters(az_engine* e, az_counters* out) {
+  if (!e || !out) return az_fail(AZ_ERR_BAD_ARG, "null argument");
+  unsigned long long c[CT_COUNT];
+  rt_d2h(e->rt, c, e->E.counters, sizeof(c));
+  out->simulations = c[CT_SIMS];
+  out->evaluations = c[CT_EVALS];
+  out->moves = c[CT_MOVES];
+  out->games = c[CT_GAMES];
+  out->nodes = c[CT_NODES];
+  out->depth_sum = c[CT_DEPTH];
+  out->descents = c[CT_DESCENTS];
+  out->samples = c[CT_SAMPLES];
+  out->ring_dropped = c[CT_DROPPED];
+  out->errors = c[CT_ERRORS];
+  out->kernel_launches = e->rt.launches;
+  out->ticks = 0;
+  return AZ_OK;
+}
+
+extern "C" int az_drain_games(az_engine* e, az_game_record* records, int32_t max_games, int32_t* n_games, int8_t* states,
+                              float* pis, float* values, int32_t max_samples, int32_t* n_samples) {
+  if (!e || !n_games || !n_samples) return az_fail(AZ_ERR_BAD_ARG, "null argument");
+  const AzDims& d = e->E.d;
+  int rc = rt_sync(e->rt);
+  if (rc) return rc;
+  unsigned long long c[CT_COUNT];
+  rt_d2h(e->rt, c, e->E.counters, sizeof(c));
+  const unsigned long long head = c[CT_GAMES_HEAD];
+  if (head - e->drained_games > AZ_GAMES_RING) e->drained_games = head - AZ_GAMES_RING;
+  int ng = 0, ns = 0;
+  while (e->drained_games < head && ng < max_games) {
+    int32_t gr[GR_INTS];
+    rt_d2h(e->rt, gr, e->E.games_ring + (size_t)(e->drained_games % AZ_GAMES_RING) * GR_INTS, sizeof(gr));
+    const int len = gr[GR_LEN];
+    if (ns + len > max_samples) break;
+    if (records) {
+      az_game_record& r = records[ng];
+      r.slot = gr[GR_SLOT];
+      r.game_length = len;
+      r.winner = ext_player(d, gr[GR_WINNER]);
+      r.by_resign = gr[GR_BY_RESIGN];
+      memcpy(&r.score, &gr[GR_SCORE_BITS], 4);
+      r.num_passes = gr[GR_PASSES];
+      r.is_resign_disabled = gr[GR_RESIGN_DISABLED];
+      r.is_marked_for_resign = gr[GR_MARKED_FOR_RESIGN];
+      r.is_could_won = gr[GR_COULD_WON];
+      r.marked_resign_player = ext_player(d, gr[GR_MARKED_PLAYER]);
+      r.first_sample = ns;
+      r.reserved = gr[GR_UID];
+    }
+    unsigned long long first = (unsigned long long)(uint32_t)gr[GR_FIRST_SAMPLE];
+    // ring positions of this game's samples (monotonic head recorded modulo 2^31; ring_cap divides nothing special)
+    for (int i = 0; i < len; ++i) {
+      const size_t slot = (size_t)((first + i) % (unsigned long long)d.ring_cap);
+      if (states) rt_d2h(e->rt, states + (size_t)(ns + i) * d.obs_bytes, e->E.r_obs + slot * d.obs_bytes, d.obs_bytes);
+      if (pis) rt_d2h(e->rt, pis + (size_t)(ns + i) * d.A, e->E.r_pi + slot * d.A, d.A * sizeof(float));
+      if (values) rt_d2h(e->rt, values + ns + i, e->E.r_z + slot, sizeof(float));
+    }
+    ns += len;
+    ng++;
+    e->drained_games++;
+  }
+  *n_games = ng;
+  *n_samples = ns;
+  return AZ_OK;
+}
+
+extern "C" int az_sample_ring_device(az_engine* e, void** states, void** pis, void** values, int64_t* head, int32_t* capacity) {
+  if (!e) return az_fail(AZ_ERR_BAD_ARG, "null engine");
+  if (states) *states = e->E.r_obs;
+  if (pis) *pis = e->E.r_pi;
+  if (values) *values = e->E.r_z;
+  if (capacity) *capacity = e->E.d.ring_cap;
+  if (head) {
+    unsigned long long c[CT_COUNT];
+    rt_d2h(e->rt, c, e->E.counters, sizeof(c));
+    *head = (int64_t)c[CT_RING_HEAD];
+  }
+  return AZ_OK;
+}
+
+extern "C" int az_stream(az_engine* e, void** cuda_stream) {
+  if (!e || !cuda_stream) return az_fail(AZ_ERR_BAD_ARG, "null argument");
+  *cuda_stream = (void*)e->rt.stream;
+  return AZ_OK;
+}
+
+extern "C" int az_last_net_ms(az_engine* e, float* ms, int32_t* n_evals) {
+  if (!e || !ms) return az_fail(AZ_ERR_BAD_ARG, "null argument");
+#ifndef AZ_EMU
+  cudaEventSynchronize(e->ev1);
+  float t = 0.f;
+  if (cudaEventElapsedTime(&t, e->ev0, e->ev1) != cudaSuccess) t = 0.f;
+  *ms = t;
+  int32_t tot[2] = {0, 0};
+  rt_d2h(e->rt, tot, e->E.leaf_total, sizeof(tot));
+  if (n_evals) *n_evals = tot[0];
+#else
+  *ms = 0.f;
+  if (n_evals) *n_evals = 0;
+#endif
+  return AZ_OK;
+}

@@ -1,0 +1,271 @@
+// az_kernels.cuh — __global__ entry points: one warp per game slot (4 warps per CTA, scratch position
+// in dynamic shared memory), plus the small bookkeeping kernels around the evaluator.
+#pragma once
+#include "az_rt.h"
+#include "az_tree.cuh"
+
+#define AZ_WPB 4  // warps (games) per CTA
+
+#ifdef AZ_EMU
+#include <vector>
+#define AZ_GLOBAL static void
+#define AZ_WARP_INDEX(nwarps) for (int az_g = 0; az_g < (nwarps); ++az_g)
+#define AZ_THREAD_LOOP(i, n) for (long long i = 0; i < (long long)(n); ++i)
+static inline unsigned char* az_emu_scratch(size_t bytes) {
+  static thread_local std::vector<unsigned char> buf;
+  if (buf.size() < bytes) buf.resize(bytes);
+  return buf.data();
+}
+#define AZ_SCRATCH(d, S) sim_carve((d), (S), az_emu_scratch(sim_bytes(d) + 64))
+#define AZ_LAUNCH_WARPS(rt, kern, nwarps, d, ...) \
+  do { (rt).launches++; kern(__VA_ARGS__, (nwarps)); } while (0)
+#define AZ_LAUNCH_THREADS(rt, kern, n, ...) \
+  do { (rt).launches++; kern(__VA_ARGS__, (n)); } while (0)
+#else
+#define AZ_GLOBAL __global__ void
+#define AZ_WARP_INDEX(nwarps)                                                  \
+  const int az_g = blockIdx.x * (blockDim.x >> 5) + (int)(threadIdx.x >> 5);   \
+  if (az_g < (nwarps))
+#define AZ_THREAD_LOOP(i, n)                                                              \
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)(n); \
+       i += (long long)gridDim.x * blockDim.x)
+static __host__ __device__ inline size_t az_sim_stride(const AzDims& d) { return ((size_t)d.ncp * 15 + d.Ap + 15) & ~(size_t)15; }
+#define AZ_SCRATCH(d, S)                                        \
+  extern __shared__ __align__(16) unsigned char az_smem[];      \
+  sim_carve((d), (S), az_smem + (threadIdx.x >> 5) * az_sim_stride(d))
+#define AZ_LAUNCH_WARPS(rt, kern, nwarps, d, ...)                                                           \
+  do {                                                                                                       \
+    (rt).launches++;                                                                                         \
+    kern<<<((nwarps) + AZ_WPB - 1) / AZ_WPB, AZ_WPB * 32, AZ_WPB * az_sim_stride(d), (rt).stream>>>(__VA_ARGS__, (nwarps)); \
+  } while (0)
+#define AZ_LAUNCH_THREADS(rt, kern, n, ...)                                                  \
+  do {                                                                                        \
+    (rt).launches++;                                                                          \
+    long long _b = ((long long)(n) + 255) / 256;                                              \
+    if (_b < 1) _b = 1;                                                                       \
+    if (_b > 148 * 16) _b = 148 * 16;                                                         \
+    kern<<<(int)_b, 256, 0, (rt).stream>>>(__VA_ARGS__, (n));                                 \
+  } while (0)
+#endif
+
+AZ_DEV void flush_counters(const AzState& E, const LocalCounters& lc) {
+  W_LANE0 {
+    if (lc.sims) atomic_add_u64(&E.counters[CT_SIMS], lc.sims);
+    if (lc.evals) atomic_add_u64(&E.counters[CT_EVALS], lc.evals);
+    if (lc.nodes) atomic_add_u64(&E.counters[CT_NODES], lc.nodes);
+    if (lc.depth) atomic_add_u64(&E.counters[CT_DEPTH], lc.depth);
+    if (lc.descents) atomic_add_u64(&E.counters[CT_DESCENTS], lc.descents);
+    if (lc.errors) atomic_add_u64(&E.counters[CT_ERRORS], lc.errors);
+  }
+}
+
+AZ_GLOBAL k_collect(AzState E, int nwarps) {
+  AZ_WARP_INDEX(nwarps) {
+    Sim S;
+    AZ_SCRATCH(E.d, S);
+    LocalCounters lc = {0, 0, 0, 0, 0, 0};
+    game_collect(E, az_g, S, lc);
+    flush_counters(E, lc);
+  }
+}
+
+AZ_GLOBAL k_apply(AzState E, int nwarps) {
+  AZ_WARP_INDEX(nwarps) {
+    LocalCounters lc = {0, 0, 0, 0, 0, 0};
+    game_apply(E, az_g, lc);
+    flush_counters(E, lc);
+  }
+}
+
+AZ_GLOBAL k_advance(AzState E, int nwarps) {
+  AZ_WARP_INDEX(nwarps) {
+    Sim S;
+    AZ_SCRATCH(E.d, S);
+    game_advance(E, az_g, S);
+  }
+}
+
+AZ_GLOBAL k_selfplay_begin(AzState E, int nwarps) {
+  AZ_WARP_INDEX(nwarps) {
+    Sim S;
+    AZ_SCRATCH(E.d, S);
+    game_new(E, az_g, S);
+    W_LANE0 E.tree_i[(size_t)az_g * TREE_INTS + TI_ACTIVE] = 1;
+  }
+}
+
+AZ_GLOBAL k_env_reset(AzState E, const int32_t* slots, int nwarps) {
+  AZ_WARP_INDEX(nwarps) {
+    Sim S;
+    AZ_SCRATCH(E.d, S);
+    const int g = slots[az_g];
+    env_reset(E, g, S);
+    W_LANE0 {
+      int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
+      ti[TI_STATE] = ST_IDLE;
+      ti[TI_NODES] = 0;
+      ti[TI_ACTIVE] = 0;
+    }
+  }
+}
+
+// step() with the reference's validation order (go.py:90-95): game over, out of range, illegal.
+AZ_GLOBAL k_env_step(AzState E, const int32_t* slots, const int32_t* actions, int32_t* out, int nwarps) {
+  AZ_WARP_INDEX(nwarps) {
+    Sim S;
+    AZ_SCRATCH(E.d, S);
+    const int g = slots[az_g];
+    const int a = actions[az_g];
+    const int32_t* ei = E.env_i + (size_t)g * ENV_INTS;
+    int err = 0;
+    const bool resign = (a == -1 && E.d.game == 0);
+    if (ei[EI_DONE]) err = -4;
+    else if (!resign && (a < 0 || a >= E.d.A)) err = -2;
+    else if (!resign && E.root_legal[(size_t)g * E.d.Ap + a] != 1) err = -3;
+    int rx2 = 0, done = 0;
+    if (!err) {
+      const StepOut o = env_step(E, g, S, a);
+      rx2 = o.reward_x2;
+      done = o.done;
+      W_LANE0 {  // the position moved: any tree of this slot that was not re-rooted is stale
+        int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
+        (void)ti;
+      }
+    }
+    W_LANE0 { out[az_g * 3] = err; out[az_g * 3 + 1] = rx2; out[az_g * 3 + 2] = done; }
+  }
+}
+
+AZ_GLOBAL k_env_obs(AzState E, int slot, int8_t* out, int nwarps) {
+  AZ_WARP_INDEX(nwarps) {
+    Sim S;
+    AZ_SCRATCH(E.d, S);
+    sim_load(E, slot, S);
+    sim_write_obs(E.d, S, out);
+  }
+}
+
+AZ_GLOBAL k_env_score(AzState E, int slot, float* out, int nwarps) {
+  AZ_WARP_INDEX(nwarps) {
+    Sim S;
+    AZ_SCRATCH(E.d, S);
+    sim_load(E, slot, S);
+    const float sc = E.d.game == 0 ? go_score(E.d, S) : 0.f;
+    W_LANE0 out[0] = sc;
+  }
+}
+
+AZ_GLOBAL k_env_copy(AzState E, int src, int dst, int nwarps) {
+  AZ_WARP_INDEX(nwarps) {
+    const AzDims& d = E.d;
+    W_FOR(c, d.ncp) E.board[(size_t)dst * d.ncp + c] = E.board[(size_t)src * d.ncp + c];
+    W_FOR(c, 8 * d.ncp) E.hist[(size_t)dst * 8 * d.ncp + c] = E.hist[(size_t)src * 8 * d.ncp + c];
+    W_FOR(c, ENV_INTS) E.env_i[(size_t)dst * ENV_INTS + c] = E.env_i[(size_t)src * ENV_INTS + c];
+    W_FOR(c, d.Ap) E.root_legal[(size_t)dst * d.Ap + c] = E.root_legal[(size_t)src * d.Ap + c];
+    W_LANE0 {
+      int32_t* ti = E.tree_i + (size_t)dst * TREE_INTS;
+      ti[TI_STATE] = ST_IDLE;
+      ti[TI_NODES] = 0;
+      ti[TI_ACTIVE] = 0;
+    }
+  }
+}
+
+AZ_GLOBAL k_clear_active(AzState E, int n) {
+  AZ_THREAD_LOOP(i, n) E.tree_i[(size_t)i * TREE_INTS + TI_ACTIVE] = 0;
+}
+
+// Arm a split-phase search on slots[]; reuse[i] keeps the re-rooted subtree (root_node argument).
+AZ_GLOBAL k_search_begin(AzState E, const int32_t* slots, const int32_t* reuse, int warm, int nwarps) {
+  AZ_WARP_INDEX(nwarps) {
+    const int g = slots[az_g];
+    int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
+    const bool keep = reuse[az_g] != 0 && ti[TI_NODES] > 0;
+    W_LANE0 {
+      ti[TI_ACTIVE] = 1;
+      ti[TI_WARM] = warm;
+      ti[TI_STATE] = keep ? ST_SEARCH_INIT : ST_NEED_ROOT;
+    }
+    w_sync();
+    if (keep) search_enter(E, g);
+  }
+}
+
+AZ_GLOBAL k_commit(AzState E, int slot, int move, double* out, int nwarps) {
+  AZ_WARP_INDEX(nwarps) {
+    double bq = 0.0;
+    const int kept = game_commit(E, slot, move, &bq);
+    W_LANE0 { out[0] = bq; out[1] = (double)kept; E.tree_i[(size_t)slot * TREE_INTS + TI_ACTIVE] = 0; }
+  }
+}
+
+// Compact the occupied leaf rows (slot-major, ascending) for the evaluator; count running searches.
+#ifdef AZ_EMU
+static void k_compact(AzState E, int n) {
+  int total = 0, running = 0;
+  for (int g = 0; g < n; ++g) {
+    const int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
+    const int c = ti[TI_ACTIVE] ? ti[TI_NLEAVES] : 0;
+    E.leaf_count[g] = c;
+    for (int j = 0; j < c; ++j) E.leaf_rows[total++] = g * E.d.Pmax + j;
+    const int st = ti[TI_STATE];
+    if (ti[TI_ACTIVE] && (st == ST_NEED_ROOT || st == ST_SEARCH_INIT || st == ST_SEARCHING)) running++;
+  }
+  E.leaf_total[0] = total;
+  E.leaf_total[1] = running;
+}
+#else
+__global__ void k_compact(AzState E, int n) {  // one CTA of 1024 threads
+  __shared__ int s_sum[1024];
+  __shared__ int s_run[32];
+  const int t = threadIdx.x;
+  const int per = (n + 1023) / 1024;
+  const int g0 = t * per, g1 = min(n, g0 + per);
+  int local = 0, running = 0;
+  for (int g = g0; g < g1; ++g) {
+    const int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
+    const int c = ti[TI_ACTIVE] ? ti[TI_NLEAVES] : 0;
+    E.leaf_count[g] = c;
+    local += c;
+    const int st = ti[TI_STATE];
+    if (ti[TI_ACTIVE] && (st == ST_NEED_ROOT || st == ST_SEARCH_INIT || st == ST_SEARCHING)) running++;
+  }
+  s_sum[t] = local;
+  running = w_sum_i(running);
+  if ((t & 31) == 0) s_run[t >> 5] = running;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan
+    int v = t >= off ? s_sum[t - off] : 0;
+    __syncthreads();
+    s_sum[t] += v;
+    __syncthreads();
+  }
+  int pos = s_sum[t] - local;
+  for (int g = g0; g < g1; ++g) {
+    const int c = E.leaf_count[g];
+    for (int j = 0; j < c; ++j) E.leaf_rows[pos++] = g * E.d.Pmax + j;
+  }
+  if (t == 1023) E.leaf_total[0] = s_sum[1023];
+  if (t == 0) {
+    int r = 0;
+    for (int k = 0; k < 32; ++k) r += s_run[k];
+    E.leaf_total[1] = r;
+  }
+}
+#endif
+
+AZ_GLOBAL k_gather_obs(AzState E, int8_t* dst, long long n) {  // n = total * obs_bytes
+  AZ_THREAD_LOOP(i, n) {
+    const long long row = i / E.d.obs_bytes, k = i - row * E.d.obs_bytes;
+    dst[i] = E.leaf_obs[(size_t)E.leaf_rows[row] * E.d.obs_bytes + k];
+  }
+}
+
+AZ_GLOBAL k_scatter_eval(AzState E, const float* pri, const float* val, long long n) {  // n = total * A
+  AZ_THREAD_LOOP(i, n) {
+    const long long row = i / E.d.A, a = i - row * E.d.A;
+    const size_t dst = (size_t)E.leaf_rows[row];
+    E.priors[dst * E.d.Ap + a] = pri[i];
+    if (a == 0) E.values[dst] = val[row];
+  }
+}

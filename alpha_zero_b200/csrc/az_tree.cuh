@@ -1,0 +1,566 @@
+// az_tree.cuh — PUCT search on one warp per game, over the structure-of-arrays tree in HBM.
+//
+// Reference semantics: /root/reference/alpha_zero/core/mcts_v2.py
+//   best_child + child_U/child_Q  :99-109, :142-185   -> tree_pick      (warp-shuffle argmax)
+//   expand                        :188-210            -> tree_expand
+//   backup                        :213-232            -> tree_backup
+//   add/revert_virtual_loss       :453-482            -> tree_vloss
+//   add_dirichlet_noise           :235-262            -> search_enter
+//   uct_search / parallel_uct_search loops :378-421 / :568-625 -> game_collect + game_apply
+//   generate_search_policy, move choice, re-root :265-298, :630-655 -> search_finish, game_commit, game_advance
+// and core/pipeline.py:289-382 (play_and_record_one_game) -> game_advance.
+// Float semantics that are reproduced on purpose are listed in SURVEY.md section 9 / DESIGN.md.
+#pragma once
+#include "az_board.cuh"
+
+#ifdef AZ_EMU
+AZ_DEV int az_popc(uint32_t x) { return __builtin_popcount(x); }
+#else
+AZ_DEV int az_popc(uint32_t x) { return __popc(x); }
+#endif
+
+struct TreeView {
+  float *N, *W, *P;
+  int16_t* cidx;
+  int16_t *parent, *pmove, *vloss;
+  int8_t* to_play;
+  uint8_t* expanded;
+};
+
+AZ_DEV TreeView tree_view(const AzState& E, int g, int buf) {
+  TreeView T;
+  const size_t nb = ((size_t)g * 2 + buf) * E.d.cap;
+  T.N = E.cN + nb * E.d.Ap;
+  T.W = E.cW + nb * E.d.Ap;
+  T.P = E.cP + nb * E.d.Ap;
+  T.cidx = E.cidx + nb * E.d.Ap;
+  T.parent = E.parent + nb;
+  T.pmove = E.pmove + nb;
+  T.vloss = E.nvloss + nb;
+  T.to_play = E.nto_play + nb;
+  T.expanded = E.expanded + nb;
+  return T;
+}
+
+struct LocalCounters { unsigned long long sims, evals, nodes, depth, descents, errors; };
+
+AZ_DEV void tree_init_node(const AzState& E, TreeView& T, int idx, int parent, int move, int to_play) {
+  const int Ap = E.d.Ap;
+  W_FOR(a, Ap) {
+    T.N[(size_t)idx * Ap + a] = 0.f;
+    T.W[(size_t)idx * Ap + a] = 0.f;
+    T.P[(size_t)idx * Ap + a] = 0.f;
+    T.cidx[(size_t)idx * Ap + a] = -1;
+  }
+  W_LANE0 {
+    T.parent[idx] = (int16_t)parent;
+    T.pmove[idx] = (int16_t)move;
+    T.to_play[idx] = (int8_t)to_play;
+    T.expanded[idx] = 0;
+    T.vloss[idx] = 0;
+  }
+}
+
+// Lazy child creation at selection time (mcts_v2.py:182-183).
+AZ_DEV int tree_new_node(const AzState& E, TreeView& T, int g, int parent, int move, int to_play, LocalCounters& lc) {
+  int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
+  const int idx = ti[TI_NODES];
+  if (idx >= E.d.cap) { lc.errors++; return -1; }
+  tree_init_node(E, T, idx, parent, move, to_play);
+  W_LANE0 {
+    T.cidx[(size_t)parent * E.d.Ap + move] = (int16_t)idx;
+    ti[TI_NODES] = idx + 1;
+  }
+  w_sync();
+  lc.nodes++;
+  return idx;
+}
+
+// argmax_a ( -Q(a) + U(a) ) over legal a with numpy's float semantics; lowest index wins ties.
+AZ_DEV int tree_pick(const AzState& E, const TreeView& T, int g, int node, const uint8_t* legal) {
+  const int Ap = E.d.Ap;
+  const int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
+  double pbc;
+  int n_i;
+  bool use64 = false;
+  if (node == 0) {
+    n_i = (int)E.root_nw[(size_t)g * 2];
+    if (n_i >= E.d.table_len) n_i = E.d.table_len - 1;
+    pbc = ti[TI_ROOT_FRESH] ? E.pbc_fresh[n_i] : E.pbc_f32[n_i];
+    use64 = ti[TI_ROOT_NOISED] != 0;
+  } else {
+    n_i = (int)T.N[(size_t)T.parent[node] * Ap + T.pmove[node]];
+    if (n_i >= E.d.table_len) n_i = E.d.table_len - 1;
+    pbc = E.pbc_f32[n_i];
+  }
+  const float pbc32 = (float)pbc;                 // Python float * float32 array -> float32 (mcts_v2.py:102)
+  const float s32 = (float)E.sqrt_tab[n_i];       // math.sqrt(N) / float32 array -> float32
+  const float* rN = T.N + (size_t)node * Ap;
+  const float* rW = T.W + (size_t)node * Ap;
+  const float* rP = T.P + (size_t)node * Ap;
+  const double* p64 = E.root_p64 + (size_t)g * Ap;
+  double best = -1e300;
+  int bi = 1 << 30;
+  W_FOR(a, E.d.A) {
+    const float n_a = rN[a];
+    const float ratio = f_div(s32, f_add(1.0f, n_a));
+    const float q = f_div(rW[a], n_a > 0.f ? n_a : 1.0f);
+    double sc;
+    if (use64) sc = d_add((double)(-q), d_mul(d_mul(pbc, p64[a]), (double)ratio));
+    else sc = (double)f_add(-q, f_mul(f_mul(pbc32, rP[a]), ratio));
+    if (legal[a] != 1) sc = -9999.0;
+    if (sc > best) { best = sc; bi = a; }
+  }
+  w_argmax(best, bi);
+  return bi;
+}
+
+AZ_DEV void root_add_w(const AzState& E, int g, bool fresh, float v) {
+  double* nw = E.root_nw + (size_t)g * 2;
+  nw[1] = fresh ? (nw[1] + (double)v) : (double)f_add((float)nw[1], v);
+}
+
+AZ_DEV void tree_backup(const AzState& E, TreeView& T, int g, int node, float value, LocalCounters& lc) {
+  const int Ap = E.d.Ap;
+  W_LANE0 {
+    float v = value;
+    while (node != 0) {
+      const size_t k = (size_t)T.parent[node] * Ap + T.pmove[node];
+      T.N[k] = f_add(T.N[k], 1.0f);
+      T.W[k] = f_add(T.W[k], v);
+      node = T.parent[node];
+      v = -v;
+    }
+    E.root_nw[(size_t)g * 2] += 1.0;
+    root_add_w(E, g, E.tree_i[(size_t)g * TREE_INTS + TI_ROOT_FRESH] != 0, v);
+  }
+  w_sync();
+  lc.sims++;
+}
+
+// sign=+1: add_virtual_loss; sign=-1: revert_virtual_loss.  W only, N untouched, float32 arithmetic.
+AZ_DEV void tree_vloss(const AzState& E, TreeView& T, int g, int node, int sign) {
+  const int Ap = E.d.Ap;
+  W_LANE0 {
+    const bool fresh = E.tree_i[(size_t)g * TREE_INTS + TI_ROOT_FRESH] != 0;
+    for (;;) {
+      bool touch = true;
+      if (sign > 0) T.vloss[node] += 1;
+      else if (T.vloss[node] > 0) T.vloss[node] -= 1;
+      else touch = false;
+      if (touch) {
+        if (node == 0) root_add_w(E, g, fresh, (float)sign);
+        else {
+          const size_t k = (size_t)T.parent[node] * Ap + T.pmove[node];
+          T.W[k] = f_add(T.W[k], (float)sign);
+        }
+      }
+      if (node == 0) break;
+      node = T.parent[node];
+    }
+  }
+  w_sync();
+}
+
+AZ_DEV void tree_expand(const AzState& E, TreeView& T, int node, const float* prior) {
+  const int Ap = E.d.Ap;
+  W_FOR(a, E.d.A) T.P[(size_t)node * Ap + a] = prior[a];
+  W_LANE0 T.expanded[node] = 1;
+  w_sync();
+}
+
+// ---- Dirichlet(0.03) on device (self-play mode; parity mode takes host samples) -------------------
+AZ_DEV double az_gamma_small(uint64_t seed, uint64_t stream, uint64_t base, double alpha) {
+  // Marsaglia-Tsang for alpha+1, boosted by U^(1/alpha)
+  const double dd = alpha + 1.0 - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * dd);
+  double out = 0.0;
+  for (int it = 0; it < 64; ++it) {
+    const double u1 = az_u01(az_rand64(seed, stream, base + 4 * it)) + 1e-300;
+    const double u2 = az_u01(az_rand64(seed, stream, base + 4 * it + 1));
+    const double u3 = az_u01(az_rand64(seed, stream, base + 4 * it + 2)) + 1e-300;
+    const double x = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+    double v = 1.0 + cc * x;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    if (log(u3) < 0.5 * x * x + dd - dd * v + dd * log(v)) { out = dd * v; break; }
+  }
+  const double u4 = az_u01(az_rand64(seed, stream, base + 3)) + 1e-300;
+  return out * exp(log(u4) / alpha);
+}
+
+// SEARCH_INIT -> SEARCHING: mix the Dirichlet noise into the root prior (float64 result) and check
+// the loop bound once (a re-used root may already have enough visits, mcts_v2.py:568).
+AZ_DEV void search_finish(const AzState& E, int g);
+
+AZ_DEV void search_enter(const AzState& E, int g) {
+  const AzDims& d = E.d;
+  int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
+  TreeView T = tree_view(E, g, ti[TI_BUF]);
+  if (E.s.root_noise) {
+    const uint8_t* legal = E.root_legal + (size_t)g * d.Ap;
+    double* p64 = E.root_p64 + (size_t)g * d.Ap;
+    double* nz = E.noise + (size_t)g * d.Ap;
+    if (!E.s.host_noise) {
+      const uint64_t ctr = (uint64_t)ti[TI_RNG_CTR];
+      double part = 0.0;
+      W_FOR(a, d.A) {
+        const double gm = az_gamma_small(E.s.seed, ((uint64_t)ti[TI_GAME_UID] << 20) ^ (uint64_t)g, (ctr * 1024 + a) * 512, 0.03);
+        nz[a] = gm;
+        part += gm;
+      }
+      const double tot = w_sum_d(part);
+      w_sync();
+      W_FOR(a, d.A) nz[a] = tot > 0.0 ? nz[a] / tot : 1.0 / d.A;
+      W_LANE0 ti[TI_RNG_CTR] += 1;
+      w_sync();
+    }
+    const bool had = ti[TI_ROOT_NOISED] != 0;
+    W_FOR(a, d.A) {
+      const double noise = legal[a] == 1 ? nz[a] : 0.0;                       // legal * dirichlet  (mcts_v2.py:260)
+      const double base = had ? d_mul(p64[a], 0.75) : (double)f_mul(T.P[a], 0.75f);  // child_P * (1 - eps)
+      p64[a] = d_add(base, d_mul(noise, 0.25));                              //   + noise * eps   -> float64
+    }
+    W_LANE0 ti[TI_ROOT_NOISED] = 1;
+    w_sync();
+  }
+  int st = ST_SEARCHING;
+  if (E.root_nw[(size_t)g * 2] >= (double)E.s.sims_bound) { st = ST_DONE; search_finish(E, g); }
+  W_LANE0 ti[TI_STATE] = st;
+  w_sync();
+}
+
+// Search policy (mcts_v2.py:265-298), root value, deterministic move.
+AZ_DEV void search_finish(const AzState& E, int g) {
+  const AzDims& d = E.d;
+  const int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
+  TreeView T = tree_view(E, g, ti[TI_BUF]);
+  const uint8_t* legal = E.root_legal + (size_t)g * d.Ap;
+  double* pi = E.res_pi + (size_t)g * d.Ap;
+  const bool warm = ti[TI_WARM] != 0;
+  double part = 0.0, bestn = -1.0;
+  int bi = 1 << 30;
+  W_FOR(a, d.A) {
+    const double n = (double)T.N[a];
+    double v = legal[a] == 1 ? n : 0.0;
+    if (!warm) v = v * v * v * v * v;  // exponent min(5, 1/0.1); exact for integer counts
+    if (d.game == 1) v = (double)(float)v;  // Gomoku's mask is int8 -> float32 policy
+    pi[a] = v;
+    part += v;
+    if (n > bestn) { bestn = n; bi = a; }
+  }
+  const double tot = w_sum_d(part);
+  w_argmax(bestn, bi);
+  w_sync();
+  W_FOR(a, d.A) if (tot > 0.0) pi[a] = pi[a] / tot;
+  W_LANE0 {
+    const double* nw = E.root_nw + (size_t)g * 2;
+    double q = 0.0;
+    if (nw[0] > 0.0) q = ti[TI_ROOT_FRESH] ? nw[1] / nw[0] : (double)f_div((float)nw[1], (float)nw[0]);
+    E.res_q[(size_t)g * 2] = q;
+    E.res_move[g] = bi;
+  }
+  w_sync();
+}
+
+// One leaf-collection pass for slot g (mcts_v2.py:572-611 / :380-411).
+AZ_DEV void game_collect(const AzState& E, int g, Sim& S, LocalCounters& lc) {
+  const AzDims& d = E.d;
+  int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
+  const int st = ti[TI_STATE];
+  int nleaves = 0;
+  if (ti[TI_ACTIVE]) {
+    if (st == ST_NEED_ROOT) {
+      sim_load(E, g, S);
+      sim_write_obs(d, S, E.leaf_obs + (size_t)g * d.Pmax * d.obs_bytes);
+      W_LANE0 E.leaf_node[(size_t)g * d.Pmax] = 0;
+      nleaves = 1;
+    } else if (st == ST_SEARCHING) {
+      TreeView T = tree_view(E, g, ti[TI_BUF]);
+      int tries = 0;
+      while (nleaves < E.s.P && tries < E.s.tries) {
+        tries++;
+        sim_load(E, g, S);
+        int node = 0, depth = 0;
+        StepOut o;
+        o.done = 0; o.reward_x2 = 0; o.winner = 0; o.captured = 0; o.score = 0.f;
+        const uint8_t* legal = E.root_legal + (size_t)g * d.Ap;
+        bool aborted = false;
+        while (T.expanded[node]) {
+          const int a = tree_pick(E, T, g, node, legal);
+          int child = T.cidx[(size_t)node * d.Ap + a];
+          if (child < 0) {
+            child = tree_new_node(E, T, g, node, a, -S.to_play, lc);
+            if (child < 0) { aborted = true; break; }
+          }
+          node = child;
+          depth++;
+          o = sim_play(d, S, a);
+          legal = S.legal;
+          if (o.done) break;
+        }
+        if (aborted) break;
+        lc.descents++;
+        lc.depth += depth;
+        if (o.done) {  // terminal: never expanded, back up the game result (mcts_v2.py:604-608)
+          tree_backup(E, T, g, node, -(0.5f * (float)o.reward_x2), lc);
+          continue;
+        }
+        if (E.s.use_vloss) tree_vloss(E, T, g, node, +1);
+        W_LANE0 E.leaf_node[(size_t)g * d.Pmax + nleaves] = (int16_t)node;
+        sim_write_obs(d, S, E.leaf_obs + ((size_t)g * d.Pmax + nleaves) * d.obs_bytes);
+        nleaves++;
+      }
+    }
+  }
+  W_LANE0 ti[TI_NLEAVES] = nleaves;
+  lc.evals += nleaves;
+  w_sync();
+}
+
+// Consume the evaluator's output for slot g (mcts_v2.py:364-368, :613-625).
+AZ_DEV void game_apply(const AzState& E, int g, LocalCounters& lc) {
+  const AzDims& d = E.d;
+  int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
+  if (!ti[TI_ACTIVE]) return;
+  int st = ti[TI_STATE];
+  TreeView T = tree_view(E, g, ti[TI_BUF]);
+  const float* pri = E.priors + (size_t)g * d.Pmax * d.Ap;
+  const float* val = E.values + (size_t)g * d.Pmax;
+  if (st == ST_NEED_ROOT) {
+    tree_init_node(E, T, 0, -1, -1, E.env_i[(size_t)g * ENV_INTS + EI_TO_PLAY]);
+    W_LANE0 {
+      ti[TI_NODES] = 1;
+      ti[TI_ROOT_FRESH] = 1;
+      ti[TI_ROOT_NOISED] = 0;
+      E.root_nw[(size_t)g * 2] = 0.0;
+      E.root_nw[(size_t)g * 2 + 1] = 0.0;
+    }
+    w_sync();
+    tree_expand(E, T, 0, pri);
+    tree_backup(E, T, g, 0, val[0], lc);
+    lc.nodes++;
+    search_enter(E, g);
+    return;
+  }
+  if (st != ST_SEARCHING) return;
+  const int n = ti[TI_NLEAVES];
+  for (int j = 0; j < n; ++j) {
+    const int node = E.leaf_node[(size_t)g * d.Pmax + j];
+    if (E.s.use_vloss) tree_vloss(E, T, g, node, -1);
+    if (T.expanded[node]) continue;  // same leaf picked twice in this batch (mcts_v2.py:619-622)
+    tree_expand(E, T, node, pri + (size_t)j * d.Ap);
+    tree_backup(E, T, g, node, val[j], lc);
+  }
+  if (E.root_nw[(size_t)g * 2] >= (double)E.s.sims_bound) {
+    search_finish(E, g);
+    W_LANE0 ti[TI_STATE] = ST_DONE;
+    w_sync();
+  }
+}
+
+// Re-root on `move` (mcts_v2.py:643-653): the subtree of the chosen child is compacted breadth-first
+// into the slot's other node pool; siblings are dropped.  Returns 1 if a subtree was kept.
+AZ_DEV int game_commit(const AzState& E, int g, int move, double* best_child_q) {
+  const AzDims& d = E.d;
+  const int Ap = d.Ap;
+  int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
+  const int buf = ti[TI_BUF];
+  TreeView To = tree_view(E, g, buf);
+  const int child = (move >= 0 && move < d.A && ti[TI_NODES] > 0) ? To.cidx[move] : -1;
+  double bq = 0.0;
+  int kept = 0;
+  if (child >= 0) {
+    const float n_c = To.N[move], w_c = To.W[move];
+    bq = (double)(-(n_c > 0.f ? f_div(w_c, n_c) : 0.0f));
+    TreeView Tn = tree_view(E, g, buf ^ 1);
+    int16_t* remap = E.remap + (size_t)g * d.cap;
+    W_LANE0 remap[0] = (int16_t)child;
+    w_sync();
+    int count = 1;
+    for (int i = 0; i < count; ++i) {
+      const int old = remap[i];
+      int base = count;
+      for (int a0 = 0; a0 < Ap; a0 += AZ_WIDTH) {
+        const int a = a0 + AZ_LANE;
+        Tn.N[(size_t)i * Ap + a] = To.N[(size_t)old * Ap + a];
+        Tn.W[(size_t)i * Ap + a] = To.W[(size_t)old * Ap + a];
+        Tn.P[(size_t)i * Ap + a] = To.P[(size_t)old * Ap + a];
+        const int c = To.cidx[(size_t)old * Ap + a];
+        const bool has = c >= 0;
+        const uint32_t m = w_ballot(has);
+        const int ni = base + az_popc(m & w_lanemask_lt());
+        if (has) { remap[ni] = (int16_t)c; Tn.parent[ni] = (int16_t)i; Tn.pmove[ni] = (int16_t)a; }
+        Tn.cidx[(size_t)i * Ap + a] = has ? (int16_t)ni : (int16_t)-1;
+        base += az_popc(m);
+      }
+      count = base;
+      W_LANE0 {
+        Tn.expanded[i] = To.expanded[old];
+        Tn.to_play[i] = To.to_play[old];
+        Tn.vloss[i] = 0;
+        if (i == 0) { Tn.parent[0] = -1; Tn.pmove[0] = -1; }
+      }
+      w_sync();
+    }
+    W_LANE0 {
+      ti[TI_BUF] = buf ^ 1;
+      ti[TI_NODES] = count;
+      ti[TI_ROOT_FRESH] = 0;   // carried N / W are np.float32 scalars (mcts_v2.py:439-443)
+      ti[TI_ROOT_NOISED] = 0;
+      E.root_nw[(size_t)g * 2] = (double)n_c;
+      E.root_nw[(size_t)g * 2 + 1] = (double)w_c;
+    }
+    kept = 1;
+  } else {
+    W_LANE0 ti[TI_NODES] = 0;
+  }
+  W_LANE0 ti[TI_STATE] = ST_IDLE;
+  w_sync();
+  if (best_child_q) *best_child_q = bq;
+  return kept;
+}
+
+// ---- device-resident self-play: what play_and_record_one_game does between two searches ---------
+AZ_DEV void game_new(const AzState& E, int g, Sim& S) {
+  int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
+  env_reset(E, g, S);
+  W_LANE0 {
+    const unsigned long long uid = atomic_add_u64(&E.counters[CT_COUNT - 1], 1ull);
+    ti[TI_GAME_UID] = (int)uid;
+    ti[TI_GAME_PLY] = 0;
+    ti[TI_MARKED] = 0;
+    ti[TI_NODES] = 0;
+    ti[TI_STATE] = ST_NEED_ROOT;
+    ti[TI_WARM] = (0 <= E.s.warm_up_steps) ? 1 : 0;
+    // resign lottery (pipeline.py:244-246)
+    int disabled = 1;
+    if (E.d.game == 0 && E.s.resign_threshold > -1.0f) {
+      const double u = az_u01(az_rand64(E.s.seed, 0x5e5160ull + (uint64_t)g, uid));
+      if (u > (double)E.s.disable_resign_ratio) disabled = 0;
+    }
+    ti[TI_RESIGN_DISABLED] = disabled;
+  }
+  w_sync();
+}
+
+AZ_DEV void game_advance(const AzState& E, int g, Sim& S) {
+  const AzDims& d = E.d;
+  int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
+  if (!ti[TI_ACTIVE] || ti[TI_STATE] != ST_DONE) return;
+  int32_t* ei = E.env_i + (size_t)g * ENV_INTS;
+  const double* pi = E.res_pi + (size_t)g * d.Ap;
+  const uint8_t* legal = E.root_legal + (size_t)g * d.Ap;
+  const bool warm = ti[TI_WARM] != 0;
+  // ---- move choice (mcts_v2.py:630-641): rejection of pass-in-warm-up / illegal == renormalised draw
+  int move = E.res_move[g];
+  if (!E.s.deterministic) {
+    int pick = -1;
+    W_LANE0 {
+      double tot = 0.0;
+      for (int a = 0; a < d.A; ++a)
+        if (legal[a] == 1 && !(warm && a == d.pass_move)) tot += pi[a];
+      if (tot > 0.0) {
+        const double u = az_u01(az_rand64(E.s.seed, 0x30fe0000ull + (uint64_t)g, ((uint64_t)ti[TI_GAME_UID] << 12) + ei[EI_STEPS])) * tot;
+        double acc = 0.0;
+        for (int a = 0; a < d.A; ++a) {
+          if (legal[a] == 1 && !(warm && a == d.pass_move) && pi[a] > 0.0) { acc += pi[a]; pick = a; if (acc > u) break; }
+        }
+      }
+      E.res_move[g] = pick;
+    }
+    w_sync();
+    pick = E.res_move[g];
+    if (pick >= 0) move = pick;
+    else if (d.pass_move >= 0) move = d.pass_move;  // the reference would spin forever here
+  }
+  // ---- record (state, pi, to_play) (pipeline.py:323-326)
+  const int ply = ti[TI_GAME_PLY];
+  if (ply < d.max_len) {
+    sim_load(E, g, S);
+    sim_write_obs(d, S, E.g_obs + ((size_t)g * d.max_len + ply) * d.obs_bytes);
+    float* gp = E.g_pi + ((size_t)g * d.max_len + ply) * d.A;
+    W_FOR(a, d.A) gp[a] = (float)pi[a];
+    W_LANE0 E.g_to_play[(size_t)g * d.max_len + ply] = (int8_t)ei[EI_TO_PLAY];
+  }
+  // ---- resignation (pipeline.py:328-341)
+  const TreeView T = tree_view(E, g, ti[TI_BUF]);
+  const int kid = T.cidx[move];
+  const float n_c = T.N[move], w_c = T.W[move];
+  const double child_q = kid >= 0 ? (double)(-(n_c > 0.f ? f_div(w_c, n_c) : 0.0f)) : 0.0;
+  const double root_q = E.res_q[(size_t)g * 2];
+  int play = move;
+  if (d.game == 0 && ei[EI_STEPS] > E.s.check_resign_after && root_q < (double)E.s.resign_threshold &&
+      child_q < (double)E.s.resign_threshold) {
+    W_LANE0 if (ti[TI_MARKED] == 0) ti[TI_MARKED] = ei[EI_TO_PLAY];
+    if (!ti[TI_RESIGN_DISABLED]) play = -1;
+  }
+  w_sync();
+  const StepOut o = env_step(E, g, S, play);
+  W_LANE0 {
+    ti[TI_GAME_PLY] = ply + 1;
+    atomic_add_u64(&E.counters[CT_MOVES], 1ull);
+  }
+  w_sync();
+  if (!o.done) {
+    W_LANE0 ti[TI_WARM] = (ei[EI_STEPS] <= E.s.warm_up_steps) ? 1 : 0;
+    w_sync();
+    const int kept = game_commit(E, g, play, nullptr);
+    if (kept) {
+      W_LANE0 ti[TI_STATE] = ST_SEARCH_INIT;
+      w_sync();
+      search_enter(E, g);
+    } else {
+      W_LANE0 ti[TI_STATE] = ST_NEED_ROOT;
+      w_sync();
+    }
+    return;
+  }
+  // ---- game over: z (pipeline.py:349-354), emit samples + game record, recycle the slot
+  const int len = (ply + 1 < d.max_len) ? ply + 1 : d.max_len;
+  const float reward = 0.5f * (float)o.reward_x2;
+  const int last_player = ei[EI_LAST_PLAYER];
+  unsigned long long head = 0;
+  W_LANE0 {
+    head = atomic_add_u64(&E.counters[CT_RING_HEAD], (unsigned long long)len);
+    E.res_q[(size_t)g * 2 + 1] = (double)head;
+  }
+  w_sync();
+  head = (unsigned long long)E.res_q[(size_t)g * 2 + 1];
+  for (int i = 0; i < len; ++i) {
+    const size_t slot = (size_t)((head + i) % (unsigned long long)d.ring_cap);
+    const int8_t* so = E.g_obs + ((size_t)g * d.max_len + i) * d.obs_bytes;
+    int8_t* dob = E.r_obs + slot * d.obs_bytes;
+    W_FOR(k, d.obs_bytes) dob[k] = so[k];
+    const float* sp = E.g_pi + ((size_t)g * d.max_len + i) * d.A;
+    float* dp = E.r_pi + slot * d.A;
+    W_FOR(a, d.A) dp[a] = sp[a];
+    W_LANE0 {
+      float z = 0.f;
+      if (reward != 0.f) z = (E.g_to_play[(size_t)g * d.max_len + i] == last_player) ? reward : -reward;
+      E.r_z[slot] = z;
+    }
+  }
+  W_LANE0 {
+    const unsigned long long gi = atomic_add_u64(&E.counters[CT_GAMES_HEAD], 1ull);
+    int32_t* gr = E.games_ring + (size_t)(gi % AZ_GAMES_RING) * GR_INTS;
+    float sc = o.score;
+    gr[GR_SLOT] = g;
+    gr[GR_LEN] = len;
+    gr[GR_WINNER] = o.winner;
+    gr[GR_BY_RESIGN] = play < 0 ? 1 : 0;
+    gr[GR_PASSES] = ei[EI_NUM_PASSES];
+    const int disabled = ti[TI_RESIGN_DISABLED], marked = ti[TI_MARKED];
+    const int is_marked = (d.game == 0 && disabled && marked != 0) ? 1 : 0;
+    gr[GR_RESIGN_DISABLED] = disabled;
+    gr[GR_MARKED_FOR_RESIGN] = is_marked;
+    gr[GR_COULD_WON] = (is_marked && o.winner == marked) ? 1 : 0;
+    gr[GR_MARKED_PLAYER] = marked;
+    gr[GR_FIRST_SAMPLE] = (int32_t)(head % (unsigned long long)d.ring_cap);
+    gr[GR_UID] = ti[TI_GAME_UID];
+    memcpy(&gr[GR_SCORE_BITS], &sc, 4);
+    atomic_add_u64(&E.counters[CT_GAMES], 1ull);
+    atomic_add_u64(&E.counters[CT_SAMPLES], (unsigned long long)len);
+  }
+  w_sync();
+  game_new(E, g, S);
+}

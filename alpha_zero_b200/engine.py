@@ -1,0 +1,212 @@
+"""Engine: a set of game slots resident on one B200, driven through the C ABI (include/az_engine.h).
+
+This is the object underneath the reference-shaped façades (envs/, mcts.py, pipeline.py) and the API
+bench.py measures.  numpy arrays in, numpy arrays out; all compute happens in libaz_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import AzConfig, AzCounters, AzGameRecord, AzSearchParams, AzSelfplayParams, as_ptr, i32
+
+# AlphaZeroNet.state_dict() order with num_batches_tracked dropped (core/network.py:85-156)
+
+
+def state_dict_tensors(state_dict):
+    """float32 host arrays of a reference-shaped state_dict, in az_set_weights order."""
+    out = []
+    for k, v in state_dict.items():
+        if k.endswith('num_batches_tracked'):
+            continue
+        a = v.detach().cpu().numpy() if hasattr(v, 'detach') else np.asarray(v)
+        out.append(np.ascontiguousarray(a, dtype=np.float32))
+    return out
+
+
+class Engine:
+    def __init__(self, game, board_size, num_games=1, max_simulations=800, max_parallel=8, komi=7.5, max_steps=0, num_to_win=5,
+                 num_stack=8, net=None, precision='fp32', device=0, seed=1, sample_ring=0, binding=None):
+        self.b = binding if binding is not None else _lib.load()
+        self.game = {'go': _lib.GAME_GO, 'gomoku': _lib.GAME_GOMOKU}[game] if isinstance(game, str) else int(game)
+        nb, nf, fc = net if net is not None else (0, 0, 0)
+        cfg = AzConfig(self.game, board_size, num_stack, komi, max_steps, num_to_win, num_games, max_simulations, max_parallel,
+                       nb, nf, fc, {'fp32': _lib.NET_FP32, 'bf16': _lib.NET_BF16}[precision], device, seed, sample_ring, 0)
+        h = C.c_void_p()
+        self.b.check(self.b.dll.az_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.b.check(self.b.dll.az_get_config(self.h, C.byref(cfg)))
+        self.cfg = cfg
+        self.N = board_size
+        self.G = num_games
+        self.A = self.b.dll.az_num_actions(self.h)
+        self.obs_bytes = self.b.dll.az_obs_bytes(self.h)
+        self.planes = 2 * num_stack + 1
+        self.max_parallel = max_parallel
+        self._active = None
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.b.dll.az_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- network ------------------------------------------------------------------------------------
+    def set_weights(self, state_dict):
+        ts = state_dict_tensors(state_dict)
+        ptrs = (C.POINTER(C.c_float) * len(ts))(*[as_ptr(t, C.c_float) for t in ts])
+        numel = (C.c_int64 * len(ts))(*[t.size for t in ts])
+        self.b.check(self.b.dll.az_set_weights(self.h, ptrs, numel, len(ts)))
+        self.weight_bytes = int(sum(t.nbytes for t in ts))
+
+    def net_forward(self, obs):
+        obs = np.ascontiguousarray(obs, dtype=np.int8).reshape(-1, self.obs_bytes)
+        n = obs.shape[0]
+        pri = np.empty((n, self.A), dtype=np.float32)
+        val = np.empty(n, dtype=np.float32)
+        self.b.check(self.b.dll.az_net_forward(self.h, as_ptr(obs, C.c_int8), n, as_ptr(pri, C.c_float), as_ptr(val, C.c_float)))
+        return pri, val
+
+    # ---- env ----------------------------------------------------------------------------------------
+    def env_reset(self, slots):
+        s = i32(slots).ravel()
+        self.b.check(self.b.dll.az_env_reset(self.h, as_ptr(s, C.c_int32), s.size))
+
+    def env_step(self, slots, actions):
+        s, a = i32(slots).ravel(), i32(actions).ravel()
+        r = np.zeros(s.size, dtype=np.float32)
+        d = np.zeros(s.size, dtype=np.int32)
+        self.b.check(self.b.dll.az_env_step(self.h, as_ptr(s, C.c_int32), as_ptr(a, C.c_int32), s.size, as_ptr(r, C.c_float), as_ptr(d, C.c_int32)))
+        return r, d
+
+    def env_observation(self, slot):
+        out = np.empty(self.obs_bytes, dtype=np.int8)
+        self.b.check(self.b.dll.az_env_observation(self.h, int(slot), as_ptr(out, C.c_int8)))
+        return out.reshape(self.planes, self.N, self.N)
+
+    def env_legal(self, slot):
+        out = np.empty(self.A, dtype=np.uint8)
+        self.b.check(self.b.dll.az_env_legal_actions(self.h, int(slot), as_ptr(out, C.c_uint8)))
+        return out
+
+    def env_board(self, slot):
+        out = np.empty(self.N * self.N, dtype=np.int8)
+        self.b.check(self.b.dll.az_env_board(self.h, int(slot), as_ptr(out, C.c_int8)))
+        return out.reshape(self.N, self.N)
+
+    def env_scalars(self, slot):
+        out = np.zeros(11, dtype=np.int32)
+        self.b.check(self.b.dll.az_env_scalars(self.h, int(slot), as_ptr(out, C.c_int32)))
+        keys = ('to_play', 'steps', 'last_move', 'last_player', 'winner', 'done', 'ko', 'by_resign', 'caps_b', 'caps_w', 'num_passes')
+        return dict(zip(keys, (int(v) for v in out)))
+
+    def env_score(self, slot):
+        out = C.c_float()
+        self.b.check(self.b.dll.az_env_score(self.h, int(slot), C.byref(out)))
+        return float(out.value)
+
+    def env_copy(self, src, dst):
+        self.b.check(self.b.dll.az_env_copy(self.h, int(src), int(dst)))
+
+    def env_export(self, slot):
+        n = self.b.dll.az_env_state_bytes(self.h)
+        out = np.empty(n, dtype=np.uint8)
+        self.b.check(self.b.dll.az_env_export(self.h, int(slot), as_ptr(out, C.c_uint8)))
+        return out.tobytes()
+
+    def env_import(self, slot, blob):
+        buf = np.frombuffer(blob, dtype=np.uint8).copy()
+        self.b.check(self.b.dll.az_env_import(self.h, int(slot), as_ptr(buf, C.c_uint8)))
+
+    # ---- search (split phase) ---------------------------------------------------------------------
+    def search_begin(self, slots, reuse, c_puct_base, c_puct_init, num_simulations, num_parallel, root_noise=False,
+                     warm_up=False, deterministic=False, noise=None):
+        s = i32(slots).ravel()
+        r = i32(reuse).ravel()
+        p = AzSearchParams(c_puct_base, c_puct_init, int(num_simulations), int(num_parallel), int(bool(root_noise)), int(bool(deterministic)))
+        nz = None
+        if noise is not None:
+            nz = np.ascontiguousarray(noise, dtype=np.float64).reshape(s.size, self.A)
+        self.b.check(self.b.dll.az_search_begin(self.h, as_ptr(s, C.c_int32), as_ptr(r, C.c_int32), s.size, C.byref(p), int(bool(warm_up)),
+                                                as_ptr(nz, C.c_double) if nz is not None else None))
+        self._active = s.copy()
+        self._leaf_buf = np.empty((s.size * max(1, int(num_parallel)), self.obs_bytes), dtype=np.int8)
+
+    def search_select(self):
+        counts = np.zeros(self._active.size, dtype=np.int32)
+        n, act = C.c_int32(), C.c_int32()
+        self.b.check(self.b.dll.az_search_select(self.h, as_ptr(self._leaf_buf, C.c_int8), as_ptr(counts, C.c_int32), C.byref(n), C.byref(act)))
+        obs = self._leaf_buf[: n.value].reshape(n.value, self.planes, self.N, self.N)
+        return obs, counts, int(act.value)
+
+    def search_apply(self, priors, values):
+        n = 0 if priors is None else len(priors)
+        if n:
+            pri = np.ascontiguousarray(priors, dtype=np.float32).reshape(n, self.A)
+            val = np.ascontiguousarray(values, dtype=np.float32).reshape(n)
+            self.b.check(self.b.dll.az_search_apply(self.h, as_ptr(pri, C.c_float), as_ptr(val, C.c_float), n))
+        else:
+            self.b.check(self.b.dll.az_search_apply(self.h, None, None, 0))
+
+    def search_run(self):
+        self.b.check(self.b.dll.az_search_run(self.h))
+
+    def search_result(self, slot):
+        cn = np.empty(self.A, dtype=np.float32)
+        cw = np.empty(self.A, dtype=np.float32)
+        pi = np.empty(self.A, dtype=np.float64)
+        rq = C.c_double()
+        mv = C.c_int32()
+        self.b.check(self.b.dll.az_search_result(self.h, int(slot), as_ptr(cn, C.c_float), as_ptr(cw, C.c_float), as_ptr(pi, C.c_double), C.byref(rq), C.byref(mv)))
+        return dict(child_N=cn, child_W=cw, pi=pi, root_q=float(rq.value), argmax=int(mv.value))
+
+    def search_commit(self, slot, move):
+        bq, nx = C.c_double(), C.c_int32()
+        self.b.check(self.b.dll.az_search_commit(self.h, int(slot), int(move), C.byref(bq), C.byref(nx)))
+        return float(bq.value), bool(nx.value)
+
+    # ---- device-resident self-play -----------------------------------------------------------------
+    def selfplay_begin(self, num_simulations, num_parallel, c_puct_base=19652.0, c_puct_init=1.25, warm_up_steps=16,
+                       check_resign_after_steps=40, resign_threshold=-1.0, disable_resign_ratio=0.1, root_noise=True, deterministic=False):
+        sp = AzSelfplayParams(AzSearchParams(c_puct_base, c_puct_init, int(num_simulations), int(num_parallel), int(root_noise), int(deterministic)),
+                              int(warm_up_steps), int(check_resign_after_steps), float(resign_threshold), float(disable_resign_ratio))
+        self.b.check(self.b.dll.az_selfplay_begin(self.h, C.byref(sp)))
+
+    def selfplay_tick(self, n=1):
+        self.b.check(self.b.dll.az_selfplay_tick(self.h, int(n)))
+
+    def sync(self):
+        self.b.check(self.b.dll.az_sync(self.h))
+
+    def counters(self):
+        c = AzCounters()
+        self.b.check(self.b.dll.az_get_counters(self.h, C.byref(c)))
+        return {k: int(getattr(c, k)) for k, _ in AzCounters._fields_}
+
+    def drain_games(self, max_games=4096, max_samples=None):
+        max_samples = max_samples or int(self.cfg.sample_ring)
+        recs = (AzGameRecord * max_games)()
+        st = np.empty((max_samples, self.obs_bytes), dtype=np.int8)
+        pis = np.empty((max_samples, self.A), dtype=np.float32)
+        z = np.empty(max_samples, dtype=np.float32)
+        ng, ns = C.c_int32(), C.c_int32()
+        self.b.check(self.b.dll.az_drain_games(self.h, recs, max_games, C.byref(ng), as_ptr(st, C.c_int8), as_ptr(pis, C.c_float),
+                                               as_ptr(z, C.c_float), max_samples, C.byref(ns)))
+        games = [{k: getattr(recs[i], k) for k, _ in AzGameRecord._fields_} for i in range(ng.value)]
+        n = ns.value
+        return games, st[:n].reshape(n, self.planes, self.N, self.N), pis[:n], z[:n]
+
+    def stream(self):
+        p = C.c_void_p()
+        self.b.check(self.b.dll.az_stream(self.h, C.byref(p)))
+        return p.value
+
+    def last_net_ms(self):
+        ms, n = C.c_float(), C.c_int32()
+        self.b.check(self.b.dll.az_last_net_ms(self.h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)

@@ -1,0 +1,189 @@
+/*
+ * az_engine.h — C ABI of the B200 self-play engine (libaz_b200.so).
+ *
+ * The reference (michaelnny/alpha_zero) has no FFI layer: its boundary is a set of Python call
+ * signatures.  Every entry point below names the reference interface it sits behind (file:line under
+ * /root/reference/alpha_zero); alpha_zero_b200/ binds them with ctypes and re-exposes the reference's
+ * Python signatures unchanged (INTEGRATION.md shows the stub).
+ *
+ * Conventions: every call returns 0 on success, <0 on error (az_last_error() gives the message, mapped
+ * by the Python layer onto the reference's ValueError / RuntimeError texts).  The caller owns all host
+ * buffers; the engine owns all device buffers.  One engine is bound to one CUDA device and one host
+ * thread.  No callbacks into the host language.  No torch types.
+ */
+#ifndef AZ_ENGINE_H
+#define AZ_ENGINE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AZ_GAME_GO 0      /* envs/go.py:19       GoEnv     (stones +1 black / -1 white, pass = N*N, resign = -1) */
+#define AZ_GAME_GOMOKU 1  /* envs/gomoku.py:17   GomokuEnv (ids 1 black / 2 white, no pass, no resign)          */
+
+#define AZ_NET_FP32 0 /* CUDA-core fp32 tower: the parity mode (pi within 1e-3 of the reference CPU path) */
+#define AZ_NET_BF16 1 /* tcgen05 bf16 tower, f32 accumulate in TMEM: the throughput mode                   */
+
+#define AZ_OK 0
+#define AZ_ERR_INVALID_ACTION -2 /* ValueError('Invalid action...')  envs/go.py:92  */
+#define AZ_ERR_ILLEGAL_ACTION -3 /* ValueError('Illegal action...')  envs/go.py:94  */
+#define AZ_ERR_GAME_OVER -4      /* RuntimeError('Game is over...')  envs/go.py:90, core/mcts_v2.py:360 */
+#define AZ_ERR_BAD_ARG -5
+#define AZ_ERR_CUDA -6
+#define AZ_ERR_STATE -7
+#define AZ_ERR_CAPACITY -8
+
+typedef struct az_engine az_engine;
+
+typedef struct az_config {
+  int32_t game;            /* AZ_GAME_*                                                        */
+  int32_t board_size;      /* N                                                                */
+  int32_t num_stack;       /* history depth of the observation, <= 8 (envs/base.py:58-63)       */
+  float komi;              /* Go (envs/go.py:47)                                                */
+  int32_t max_steps;       /* Go; 0 -> 2*N*N (envs/go.py:49)                                    */
+  int32_t num_to_win;      /* Gomoku (envs/gomoku.py:26)                                        */
+  int32_t num_games;       /* concurrent game slots held in HBM                                 */
+  int32_t max_simulations; /* sizes the per-game node pool: nodes = max_simulations+3*max_parallel+16 */
+  int32_t max_parallel;    /* sizes the leaf batch: num_games*max_parallel rows                 */
+  int32_t num_res_blocks;  /* core/network.py:85 AlphaZeroNet(..., num_res_block, num_filters, num_fc_units, gomoku) */
+  int32_t num_filters;     /*   0 => engine without a network (external evaluator only)         */
+  int32_t num_fc_units;
+  int32_t net_precision;   /* AZ_NET_*                                                          */
+  int32_t device;          /* CUDA ordinal                                                      */
+  uint64_t seed;           /* device RNG stream (Dirichlet noise, move sampling, resign lottery) */
+  int32_t sample_ring;     /* capacity (samples) of the finished-game sample ring; 0 -> default  */
+  int32_t reserved;
+} az_config;
+
+/* Parameters of one search call == the arguments of uct_search / parallel_uct_search
+ * (core/mcts_v2.py:301-311, 485-496) and of the `act` closure (core/pipeline.py:125-156). */
+typedef struct az_search_params {
+  double c_puct_base, c_puct_init;
+  int32_t num_simulations;
+  int32_t num_parallel;  /* <=1: uct_search semantics (no virtual loss, bound = num_simulations);
+                             >1: parallel_uct_search (virtual loss, bound = num_simulations+num_parallel) */
+  int32_t root_noise;    /* add_dirichlet_noise, core/mcts_v2.py:235-262 */
+  int32_t deterministic; /* argmax(child_N) instead of sampling, core/mcts_v2.py:630-641 */
+} az_search_params;
+
+/* Parameters of the device-resident self-play loop == the arguments run_selfplay_actor_loop hands to
+ * play_and_record_one_game (core/pipeline.py:166-189, 249-259). */
+typedef struct az_selfplay_params {
+  az_search_params search;
+  int32_t warm_up_steps;            /* warm_up = steps <= warm_up_steps, core/pipeline.py:320 */
+  int32_t check_resign_after_steps; /* core/pipeline.py:328-341 */
+  float resign_threshold;           /* <= -1 disables resignation, core/pipeline.py:216,244 */
+  float disable_resign_ratio;       /* per-game lottery, core/pipeline.py:244-246 */
+} az_selfplay_params;
+
+typedef struct az_counters {
+  uint64_t simulations; /* root-visit increments (SURVEY.md 8d definition) */
+  uint64_t evaluations; /* leaves sent to the network / evaluator (duplicates included, terminals not) */
+  uint64_t moves;       /* real-game plies played by the self-play loop */
+  uint64_t games;       /* finished games */
+  uint64_t nodes;       /* tree nodes created */
+  uint64_t depth_sum;   /* sum of leaf depths (mean depth = depth_sum / descents) */
+  uint64_t descents;    /* select passes (incl. terminal hits) */
+  uint64_t samples;     /* (state, pi, z) samples written to the sample ring */
+  uint64_t ring_dropped;/* samples overwritten before the host drained them */
+  uint64_t errors;      /* sticky device-side error count (node pool exhausted, ...) */
+  uint64_t kernel_launches; /* kernels launched by this engine since creation */
+  uint64_t ticks;
+} az_counters;
+
+/* Finished-game record == the `stats` dict of play_and_record_one_game (core/pipeline.py:367-380). */
+typedef struct az_game_record {
+  int32_t slot;
+  int32_t game_length;
+  int32_t winner;         /* black id, white id, or 0 for a draw */
+  int32_t by_resign;      /* result string 'B+R' / 'W+R' */
+  float score;            /* black - (white + komi) on the final board (Go) */
+  int32_t num_passes;
+  int32_t is_resign_disabled, is_marked_for_resign, is_could_won, marked_resign_player;
+  int32_t first_sample;   /* index (monotonic) of this game's first sample in the sample ring */
+  int32_t reserved;
+} az_game_record;
+
+const char* az_last_error(void);
+int az_version(void);
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+int az_create(const az_config* cfg, az_engine** out);
+int az_destroy(az_engine* e);
+int az_get_config(az_engine* e, az_config* out);
+int az_num_actions(az_engine* e);            /* envs/base.py:65 action_dim */
+int az_obs_bytes(az_engine* e);              /* (2*num_stack+1)*N*N int8, envs/base.py:228-259 */
+
+/* ---- network weights: nn.Module.state_dict() -> engine-owned, BN-folded device buffers ----------
+ * tensors[i] are host float32 arrays in the order of AlphaZeroNet.state_dict() (core/network.py:85-156)
+ * with the num_batches_tracked entries dropped; numel[i] their element counts.  Replaces
+ * network.load_state_dict(...) + network.to(device) in run_selfplay_actor_loop (core/pipeline.py:205-214,
+ * 232-239). */
+int az_set_weights(az_engine* e, const float* const* tensors, const int64_t* numel, int32_t n_tensors);
+
+/* Network forward on host observations (eval_position, core/pipeline.py:91-123):
+ * obs int8 [n, 2*num_stack+1, N, N] -> priors float32 [n, A] (softmax over ALL actions), values float32 [n]. */
+int az_net_forward(az_engine* e, const int8_t* obs, int32_t n, float* priors, float* values);
+
+/* ---- BoardGameEnv contract (envs/base.py:26, go.py:88, gomoku.py:45) on game slots -------------- */
+int az_env_reset(az_engine* e, const int32_t* slots, int32_t n);                 /* reset() */
+/* step(): actions[i] in [0,A) or -1 (resign, Go). rewards/dones out (reward is for the mover). */
+int az_env_step(az_engine* e, const int32_t* slots, const int32_t* actions, int32_t n, float* rewards, int32_t* dones);
+int az_env_observation(az_engine* e, int32_t slot, int8_t* out);                /* observation() */
+int az_env_legal_actions(az_engine* e, int32_t slot, uint8_t* out);             /* legal_actions */
+int az_env_board(az_engine* e, int32_t slot, int8_t* out);                      /* board, reference stone ids */
+/* scalars: [to_play, steps, last_move, last_player, winner, done, ko, by_resign, caps_b, caps_w, num_passes] */
+int az_env_scalars(az_engine* e, int32_t slot, int32_t* out11);
+int az_env_score(az_engine* e, int32_t slot, float* out_score);                 /* go_engine.py:509-516 */
+int az_env_copy(az_engine* e, int32_t src_slot, int32_t dst_slot);              /* copy.deepcopy(env) */
+int az_env_state_bytes(az_engine* e);
+int az_env_export(az_engine* e, int32_t slot, uint8_t* out);                    /* pickling */
+int az_env_import(az_engine* e, int32_t slot, const uint8_t* in);
+
+/* ---- search, split phase: the evaluator lives outside (a Python eval_func, a fake, torch) --------
+ * az_search_begin : start uct_search/parallel_uct_search on `slots`; reuse[i]!=0 keeps the slot's
+ *                   re-rooted subtree (root_node argument), 0 starts from a fresh root.
+ *                   noise: float64 [n, A] host-drawn Dirichlet samples (np.random.dirichlet) or NULL
+ *                   (engine draws its own when params.root_noise).
+ * az_search_select: one leaf-collection pass (core/mcts_v2.py:568-611).  Writes the leaf observations
+ *                   int8 [total, obs_bytes] in slot-major order, counts[i] leaves for slots[i]; returns
+ *                   total in *n_leaves.  Slots whose search is complete contribute 0.
+ * az_search_apply : priors float32 [total, A], values float32 [total] in the same order: revert virtual
+ *                   loss, expand, back up (core/mcts_v2.py:613-625); updates done flags.
+ * az_search_result: child_N float32[A], pi float64[A], root_Q, best-child info of a finished search.
+ * az_search_commit: re-root on `move` (core/mcts_v2.py:643-653); returns 1 in *has_next if a subtree is kept.
+ */
+int az_search_begin(az_engine* e, const int32_t* slots, const int32_t* reuse, int32_t n, const az_search_params* p,
+                    int32_t warm_up, const double* noise);
+int az_search_select(az_engine* e, int8_t* leaf_obs, int32_t* counts, int32_t* n_leaves, int32_t* n_active);
+int az_search_apply(az_engine* e, const float* priors, const float* values, int32_t n_leaves);
+int az_search_result(az_engine* e, int32_t slot, float* child_N, float* child_W, double* pi, double* root_q,
+                     int32_t* argmax_move);
+int az_search_commit(az_engine* e, int32_t slot, int32_t move, double* best_child_q, int32_t* has_next);
+/* Same loop with the engine's own network as evaluator; runs until every begun search is complete. */
+int az_search_run(az_engine* e);
+
+/* ---- device-resident self-play (play_and_record_one_game x num_games, core/pipeline.py:289-382) --
+ * az_selfplay_begin resets every slot and arms the loop; az_selfplay_tick(n) runs n leaf batches
+ * (select -> network -> apply -> advance) without host synchronisation. */
+int az_selfplay_begin(az_engine* e, const az_selfplay_params* p);
+int az_selfplay_tick(az_engine* e, int32_t n_ticks);
+int az_sync(az_engine* e);
+int az_get_counters(az_engine* e, az_counters* out);
+/* Drain finished games: up to max_games records and their samples, oldest first.
+ * states int8 [*, obs_bytes], pis float32 [*, A], values float32 [*] (z, core/pipeline.py:349-354). */
+int az_drain_games(az_engine* e, az_game_record* records, int32_t max_games, int32_t* n_games, int8_t* states,
+                   float* pis, float* values, int32_t max_samples, int32_t* n_samples);
+/* Device pointers of the last drained-but-not-copied sample block for NCCL all-gather by the caller. */
+int az_sample_ring_device(az_engine* e, void** states, void** pis, void** values, int64_t* head, int32_t* capacity);
+/* The CUDA stream every engine kernel is launched on (bench.py times on it with its own events). */
+int az_stream(az_engine* e, void** cuda_stream);
+/* Time of the network kernels of the most recent az_selfplay_tick call, measured with CUDA events (ms). */
+int az_last_net_ms(az_engine* e, float* ms, int32_t* n_evals);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AZ_ENGINE_H */
