@@ -31,7 +31,7 @@ struct az_engine {
   std::vector<int32_t> active;  // slots of the current split-phase search, ascending
   int last_total = 0;
   bool selfplay = false;
-  unsigned long long drained_games = 0;
+  unsigned long long drained_games = 0, dropped_samples = 0;
   float last_net_ms = 0.f;
   int last_net_evals = 0;
 #ifndef AZ_EMU
@@ -241,7 +241,7 @@ extern "C" int az_net_forward(az_engine* e, const int8_t* obs, int32_t n, float*
     int32_t cnt = m;
     rt_h2d(e->rt, e->E.leaf_total + 2, &cnt, sizeof(cnt));
     int rc = aznet_forward(e->net, e->rt, e->d_stage_obs, nullptr, e->E.leaf_total + 2, m, e->E.priors, e->E.values, d.Ap);
-    if (rc) return az_fail(rc, "az_net_forward failed");
+    if (rc) return az_fail(rc, "az_net_forward: " + g_az_error);
     std::vector<float> tmp((size_t)m * d.Ap);
     rt_d2h(e->rt, tmp.data(), e->E.priors, tmp.size() * sizeof(float));
     for (int i = 0; i < m; ++i) memcpy(priors + (size_t)(off + i) * d.A, tmp.data() + (size_t)i * d.Ap, d.A * sizeof(float));
@@ -492,7 +492,7 @@ extern "C" int az_search_run(az_engine* e) {
     if (tot[1] == 0) break;
     if (tot[0] > 0) {
       rc = aznet_forward(e->net, e->rt, e->E.leaf_obs, e->E.leaf_rows, e->E.leaf_total, d.G * d.Pmax, e->E.priors, e->E.values, d.Ap);
-      if (rc) return az_fail(rc, "network forward failed");
+      if (rc) return az_fail(rc, "network forward: " + g_az_error);
     }
     AZ_LAUNCH_WARPS(e->rt, k_apply, d.G, d, e->E);
   }
@@ -545,6 +545,7 @@ extern "C" int az_selfplay_begin(az_engine* e, const az_selfplay_params* p) {
   e->active.clear();
   rt_zero(e->rt, e->E.counters, CT_COUNT * sizeof(unsigned long long));
   e->drained_games = 0;
+  e->dropped_samples = 0;
   AZ_LAUNCH_WARPS(e->rt, k_selfplay_begin, e->E.d.G, e->E.d, e->E);
   return rt_sync(e->rt);
 }
@@ -563,7 +564,7 @@ extern "C" int az_selfplay_tick(az_engine* e, int32_t n_ticks) {
     k_compact(e->E, d.G);
 #endif
     int rc = aznet_forward(e->net, e->rt, e->E.leaf_obs, e->E.leaf_rows, e->E.leaf_total, d.G * d.Pmax, e->E.priors, e->E.values, d.Ap);
-    if (rc) return az_fail(rc, "network forward failed");
+    if (rc) return az_fail(rc, "network forward: " + g_az_error);
 #ifndef AZ_EMU
     if (t == n_ticks - 1) cudaEventRecord(e->ev1, e->rt.stream);
 #endif
@@ -591,7 +592,7 @@ extern "C" int az_get_counters(az_engine* e, az_counters* out) {
   out->depth_sum = c[CT_DEPTH];
   out->descents = c[CT_DESCENTS];
   out->samples = c[CT_SAMPLES];
-  out->ring_dropped = c[CT_DROPPED];
+  out->ring_dropped = c[CT_DROPPED] + e->dropped_samples;
   out->errors = c[CT_ERRORS];
   out->kernel_launches = e->rt.launches;
   out->ticks = 0;
@@ -629,13 +630,26 @@ extern "C" int az_drain_games(az_engine* e, az_game_record* records, int32_t max
       r.first_sample = ns;
       r.reserved = gr[GR_UID];
     }
-    unsigned long long first = (unsigned long long)(uint32_t)gr[GR_FIRST_SAMPLE];
-    // ring positions of this game's samples (monotonic head recorded modulo 2^31; ring_cap divides nothing special)
-    for (int i = 0; i < len; ++i) {
-      const size_t slot = (size_t)((first + i) % (unsigned long long)d.ring_cap);
-      if (states) rt_d2h(e->rt, states + (size_t)(ns + i) * d.obs_bytes, e->E.r_obs + slot * d.obs_bytes, d.obs_bytes);
-      if (pis) rt_d2h(e->rt, pis + (size_t)(ns + i) * d.A, e->E.r_pi + slot * d.A, d.A * sizeof(float));
-      if (values) rt_d2h(e->rt, values + ns + i, e->E.r_z + slot, sizeof(float));
+    const unsigned long long first = (unsigned long long)(uint32_t)gr[GR_FIRST_LO] | ((unsigned long long)(uint32_t)gr[GR_FIRST_HI] << 32);
+    if (c[CT_RING_HEAD] - first > (unsigned long long)d.ring_cap) {  // overwritten before the host came by: drop the game
+      e->dropped_samples += (unsigned long long)len;
+      e->drained_games++;
+      continue;
+    }
+    // the samples of one game are contiguous in the ring (modulo wrap): at most two copies per array
+    const size_t s0 = (size_t)(first % (unsigned long long)d.ring_cap);
+    const size_t n1 = std::min((size_t)len, (size_t)d.ring_cap - s0), n2 = (size_t)len - n1;
+    if (states) {
+      rt_d2h(e->rt, states + (size_t)ns * d.obs_bytes, e->E.r_obs + s0 * d.obs_bytes, n1 * d.obs_bytes);
+      if (n2) rt_d2h(e->rt, states + (size_t)(ns + n1) * d.obs_bytes, e->E.r_obs, n2 * d.obs_bytes);
+    }
+    if (pis) {
+      rt_d2h(e->rt, pis + (size_t)ns * d.A, e->E.r_pi + s0 * d.A, n1 * d.A * sizeof(float));
+      if (n2) rt_d2h(e->rt, pis + (size_t)(ns + n1) * d.A, e->E.r_pi, n2 * d.A * sizeof(float));
+    }
+    if (values) {
+      rt_d2h(e->rt, values + ns, e->E.r_z + s0, n1 * sizeof(float));
+      if (n2) rt_d2h(e->rt, values + ns + n1, e->E.r_z, n2 * sizeof(float));
     }
     ns += len;
     ng++;

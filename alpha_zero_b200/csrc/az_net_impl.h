@@ -1,0 +1,46 @@
+// az_net_impl.h — internal structures shared by az_net.cu (fp32 tower, heads) and az_net_tc.cu (tcgen05 tower).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "az_net.h"
+
+struct NetGeom {
+  int n, nc, planes, obs_bytes;  // observation geometry
+  int off;                       // where the N x N observation sits inside the canvas (2 for Gomoku)
+  int Hc;                        // canvas side the tower runs on
+  int Wr;                        // row stride in cells = Hc + 1 (one zero column)
+  int RP;                        // rows per leaf = (Hc+1)*(Hc+1)
+  int guard;                     // zero rows before the first and after the last leaf
+  int cin_pad;                   // channels of the input feature rows (>= planes)
+};
+
+struct HeadParams {
+  const float *pol_w, *pol_b, *pol_fc_w, *pol_fc_b;
+  const float *val_w, *val_b, *val_fc1_w, *val_fc1_b, *val_fc2_w, *val_fc2_b;
+};
+
+struct AzNetTc;  // tensor-core tower state (az_net_tc.cu)
+
+struct AzNet {
+  int blocks = 0, C = 0, fc = 0, A = 0, precision = 0, max_leaves = 0, ready = 0;
+  NetGeom g;
+  size_t rows_total = 0;
+  void *act_in = nullptr, *act_x = nullptr, *act_mid = nullptr;
+  std::vector<float*> conv_w, conv_b;                // device, fp32 tower: [9][cin_pad][cout], [cout]
+  std::vector<std::vector<float>> host_w, host_b;    // folded host copies (source for the bf16 packing)
+  HeadParams hp;
+  std::vector<void*> allocs;
+  double flops = 0.0;
+  AzNetTc* tc = nullptr;
+};
+
+int aznet_tc_create(AzNet* n, AzRt& rt, std::string& err);
+void aznet_tc_destroy(AzNet* n);
+int aznet_tc_set_weights(AzNet* n, AzRt& rt, std::string& err);
+int aznet_tc_forward(AzNet* n, AzRt& rt, const int8_t* obs_base, const int32_t* row_list, const int32_t* n_rows_dev, int max_rows,
+                     float* priors_base, float* values_base, int pri_stride);

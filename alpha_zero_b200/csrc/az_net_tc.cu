@@ -1,0 +1,365 @@
+// az_net_tc.cu — the residual tower on 5th-generation tensor cores (sm_100a only).
+//
+// One kernel = one 3x3 convolution layer as an implicit GEMM over the padded-row activation matrix
+// (layout: az_net.cu header):   D[m, co] = sum_{tap, ci} X[m + off(tap), ci] * W[tap][co][ci]
+//   M tile 128 rows (UMMA_M = 128, cta_group::1), N = all output channels (64 / 128 / 256),
+//   K = 9 taps x Cin, consumed 64 channels (= one 128-byte swizzle atom of bf16) per pipeline stage.
+// Warp roles (192 threads, persistent over M tiles; the leaf count is read from device memory so the
+// launch never waits for the host):
+//   warp 0   TMA producer: per stage one 2-D box of activations (128 rows x 64 ch, rows shifted by the
+//            tap offset) and one of weights (N rows x 64 ch), SWIZZLE_128B, completing on an mbarrier
+//   warp 1   allocates TMEM, then one elected lane issues tcgen05.mma.kind::f16 (bf16 x bf16 -> f32)
+//            into one of two TMEM accumulator stages and commits stage-free / accumulator-full barriers
+//   warps 2-5 epilogue: tcgen05.ld the accumulator (each warp owns its 32-lane TMEM quarter), add the
+//            folded-BN bias, the residual, ReLU, force the padding rows to zero, store bf16 rows
+// The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+#include "az_net_impl.h"
+#include "az_net_kernels.cuh"
+
+#define TC_STAGES 4
+#define TC_BM 128
+#define TC_BK 64
+#define TC_THREADS 192
+
+struct AzNetTc {
+  CUtensorMap map_in, map_x, map_mid;
+  std::vector<CUtensorMap> map_w;
+  std::vector<__nv_bfloat16*> w_dev;
+  int cin0 = 64;
+  size_t smem_bytes = 0;
+  int num_sms = 148;
+};
+
+struct TcLayer {
+  int cin, cout;       // channels (cin multiple of 64)
+  int relu, has_res;
+  int Wr, Hc, RP, guard;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major operand tile, 128-byte swizzle: rows 128 B apart, 8-row atoms 1024 B apart (SBO), descriptor version 1.
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;             // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;   // stride byte offset
+  d |= (uint64_t)1 << 46;             // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;             // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const float* __restrict__ bias,
+          const __nv_bfloat16* res, __nv_bfloat16* out, const int32_t* __restrict__ n_rows, TcLayer L) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // carve: stages of {A 16 KB, B cout*128 B}, then barriers
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t a_bytes = TC_BM * TC_BK * 2, b_bytes = (uint32_t)L.cout * TC_BK * 2, stage_bytes = a_bytes + b_bytes;
+  uint64_t* full_bar = (uint64_t*)(smem + (size_t)TC_STAGES * stage_bytes);
+  uint64_t* empty_bar = full_bar + TC_STAGES;
+  uint64_t* tfull_bar = empty_bar + TC_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long M = (long long)(*n_rows) * L.RP;
+  const int num_tiles = (int)((M + TC_BM - 1) / TC_BM);
+  const int kc = L.cin / TC_BK, KS = 9 * kc;
+  uint32_t tmem_cols = 2 * (uint32_t)L.cout;  // two accumulator stages
+  tmem_cols = tmem_cols <= 32 ? 32 : tmem_cols <= 64 ? 64 : tmem_cols <= 128 ? 128 : tmem_cols <= 256 ? 256 : 512;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int row0 = L.guard + t * TC_BM;
+        for (int ks = 0; ks < KS; ++ks) {
+          const int tap = ks / kc, kk = ks - tap * kc;
+          const int toff = (tap / 3 - 1) * L.Wr + (tap % 3 - 1);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          unsigned char* sa = smem + (size_t)stage * stage_bytes;
+          tma_load_2d(sa, &map_a, &full_bar[stage], kk * TC_BK, row0 + toff);
+          tma_load_2d(sa + a_bytes, &map_b, &full_bar[stage], kk * TC_BK, tap * L.cout);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(L.cout >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * L.cout);
+        for (int ks = 0; ks < KS; ++ks) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint64_t adesc = tc_smem_desc(sa), bdesc = tc_smem_desc(sa + a_bytes);
+#pragma unroll
+          for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
+            // advance 16 bf16 = 32 bytes inside the swizzle atom: +2 in the (>>4) start-address field
+            tc_mma(d_tmem, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), idesc, (ks | k4) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull_bar[acc]);
+      }
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+      tc_fence_after();
+      const long long m = (long long)t * TC_BM + q * 32 + lane;
+      const int r = (int)(m % L.RP);
+      const int yy = r / L.Wr, xx = r - yy * L.Wr;
+      const bool valid = (m < M) && yy < L.Hc && xx < L.Hc;
+      const size_t grow = ((size_t)L.guard + (size_t)m) * L.cout;
+      for (int c0 = 0; c0 < L.cout; c0 += 32) {
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * L.cout + c0), v);
+        if (m < M) {
+          __align__(16) __nv_bfloat16 o[32];
+          if (valid) {
+            __align__(16) __nv_bfloat16 rr[32];
+            if (L.has_res) {
+              const uint4* rp = reinterpret_cast<const uint4*>(res + grow + c0);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) reinterpret_cast<uint4*>(rr)[k] = rp[k];
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float f = __uint_as_float(v[j]) + bias[c0 + j];
+              if (L.has_res) f += __bfloat162float(rr[j]);
+              if (L.relu) f = fmaxf(f, 0.f);
+              o[j] = __float2bfloat16(f);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __float2bfloat16(0.f);
+          }
+          uint4* op = reinterpret_cast<uint4*>(out + grow + c0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) op[k] = reinterpret_cast<const uint4*>(o)[k];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* m, void* base, uint64_t inner, uint64_t rows, uint32_t box_rows, std::string& err) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { err = "cuTensorMapEncodeTiled not available"; return AZ_ERR_CUDA; }
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {inner * 2};
+  cuuint32_t box[2] = {TC_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r); return AZ_ERR_CUDA; }
+  return 0;
+}
+
+int aznet_tc_create(AzNet* n, AzRt& rt, std::string& err) {
+  AzNetTc* tc = new AzNetTc();
+  n->tc = tc;
+  // the bf16 tower reads 64-channel input rows (one swizzle atom); re-allocate the input buffer accordingly
+  n->g.cin_pad = 64;
+  rt_free(n->act_in);
+  n->act_in = rt_alloc(n->rows_total * 64 * 2);
+  if (!n->act_in) { err = "out of device memory"; return AZ_ERR_CUDA; }
+  if (n->C != 64 && n->C != 128 && n->C != 256) { err = "bf16 tower supports num_filters 64, 128 or 256"; return AZ_ERR_BAD_ARG; }
+  int rc = make_map(&tc->map_in, n->act_in, 64, n->rows_total, TC_BM, err);
+  if (!rc) rc = make_map(&tc->map_x, n->act_x, n->C, n->rows_total, TC_BM, err);
+  if (!rc) rc = make_map(&tc->map_mid, n->act_mid, n->C, n->rows_total, TC_BM, err);
+  if (rc) return rc;
+  tc->smem_bytes = (size_t)TC_STAGES * (TC_BM * TC_BK * 2 + (size_t)n->C * TC_BK * 2) + 1024 + 256;
+  cudaError_t e = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc->smem_bytes);
+  if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return AZ_ERR_CUDA; }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&tc->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  return 0;
+}
+
+void aznet_tc_destroy(AzNet* n) {
+  if (!n || !n->tc) return;
+  for (auto* p : n->tc->w_dev) rt_free(p);
+  delete n->tc;
+  n->tc = nullptr;
+}
+
+// Pack folded fp32 weights [9][cin_pad][cout] into bf16 [9][cout][cin] (K-major B operand) and build their TMA maps.
+int aznet_tc_set_weights(AzNet* n, AzRt& rt, std::string& err) {
+  AzNetTc* tc = n->tc;
+  for (auto* p : tc->w_dev) rt_free(p);
+  tc->w_dev.clear();
+  tc->map_w.clear();
+  const int C = n->C;
+  for (size_t li = 0; li < n->host_w.size(); ++li) {
+    const int cin_src = li == 0 ? n->g.cin_pad : C;  // layer 0 was folded with the input rows' channel padding (64 here)
+    const int cin = li == 0 ? 64 : C;
+    const std::vector<float>& w = n->host_w[li];
+    std::vector<__nv_bfloat16> pk((size_t)9 * C * cin, __float2bfloat16(0.f));
+    for (int t = 0; t < 9; ++t)
+      for (int ci = 0; ci < cin_src; ++ci)
+        for (int co = 0; co < C; ++co) pk[((size_t)t * C + co) * cin + ci] = __float2bfloat16(w[((size_t)t * cin_src + ci) * C + co]);
+    __nv_bfloat16* d = (__nv_bfloat16*)rt_alloc(pk.size() * 2);
+    if (!d) { err = "out of device memory"; return AZ_ERR_CUDA; }
+    rt_h2d(rt, d, pk.data(), pk.size() * 2);
+    tc->w_dev.push_back(d);
+    CUtensorMap m;
+    int rc = make_map(&m, d, (uint64_t)cin, (uint64_t)9 * C, (uint32_t)C, err);
+    if (rc) return rc;
+    tc->map_w.push_back(m);
+  }
+  return 0;
+}
+
+int aznet_tc_forward(AzNet* n, AzRt& rt, const int8_t* obs_base, const int32_t* row_list, const int32_t* n_rows_dev, int max_rows,
+                     float* priors_base, float* values_base, int pri_stride) {
+  AzNetTc* tc = n->tc;
+  const NetGeom& g = n->g;
+  {
+    long long work = (long long)max_rows * g.nc;
+    int blocks = (int)std::min<long long>((work + 255) / 256, 148 * 8);
+    k_net_input<__nv_bfloat16><<<blocks, 256, 0, rt.stream>>>(obs_base, row_list, n_rows_dev, (__nv_bfloat16*)n->act_in, g);
+    rt.launches++;
+  }
+  const long long Mmax = (long long)max_rows * g.RP;
+  const int grid = (int)std::min<long long>((Mmax + TC_BM - 1) / TC_BM, tc->num_sms);
+  TcLayer L;
+  L.Wr = g.Wr; L.Hc = g.Hc; L.RP = g.RP; L.guard = g.guard;
+  __nv_bfloat16* X = (__nv_bfloat16*)n->act_x;
+  __nv_bfloat16* MID = (__nv_bfloat16*)n->act_mid;
+  L.cin = 64; L.cout = n->C; L.relu = 1; L.has_res = 0;
+  k_conv_tc<<<grid, TC_THREADS, tc->smem_bytes, rt.stream>>>(tc->map_in, tc->map_w[0], n->conv_b[0], nullptr, X, n_rows_dev, L);
+  rt.launches++;
+  L.cin = n->C;
+  for (int b = 0; b < n->blocks; ++b) {
+    L.relu = 1; L.has_res = 0;
+    k_conv_tc<<<grid, TC_THREADS, tc->smem_bytes, rt.stream>>>(tc->map_x, tc->map_w[1 + 2 * b], n->conv_b[1 + 2 * b], nullptr, MID, n_rows_dev, L);
+    L.relu = 1; L.has_res = 1;
+    k_conv_tc<<<grid, TC_THREADS, tc->smem_bytes, rt.stream>>>(tc->map_mid, tc->map_w[2 + 2 * b], n->conv_b[2 + 2 * b], X, X, n_rows_dev, L);
+    rt.launches += 2;
+  }
+  const int HW = g.Hc * g.Hc;
+  const size_t head_smem = (size_t)(3 * HW + n->fc + n->A) * sizeof(float);
+  k_heads<__nv_bfloat16><<<max_rows, 128, head_smem, rt.stream>>>(X, row_list, n_rows_dev, n->hp, g, n->C, n->A, n->fc, priors_base, values_base, pri_stride);
+  rt.launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_az_error = std::string("tensor-core tower launch: ") + cudaGetErrorString(e); return AZ_ERR_CUDA; }
+  return AZ_OK;
+}

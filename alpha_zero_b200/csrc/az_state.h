@@ -133,5 +133,5 @@ enum { CT_SIMS = 0, CT_EVALS, CT_MOVES, CT_GAMES, CT_NODES, CT_DEPTH, CT_DESCENT
        CT_RING_HEAD, CT_GAMES_HEAD, CT_COUNT = 16 };
 
 enum { GR_SLOT = 0, GR_LEN, GR_WINNER, GR_BY_RESIGN, GR_SCORE_BITS, GR_PASSES, GR_RESIGN_DISABLED, GR_MARKED_FOR_RESIGN,
-       GR_COULD_WON, GR_MARKED_PLAYER, GR_FIRST_SAMPLE, GR_UID, GR_INTS = 12 };
+       GR_COULD_WON, GR_MARKED_PLAYER, GR_FIRST_LO, GR_FIRST_HI, GR_UID, GR_INTS = 16 };
 #define AZ_GAMES_RING 4096

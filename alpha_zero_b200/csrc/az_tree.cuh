@@ -555,7 +555,8 @@ AZ_DEV void game_advance(const AzState& E, int g, Sim& S) {
     gr[GR_MARKED_FOR_RESIGN] = is_marked;
     gr[GR_COULD_WON] = (is_marked && o.winner == marked) ? 1 : 0;
     gr[GR_MARKED_PLAYER] = marked;
-    gr[GR_FIRST_SAMPLE] = (int32_t)(head % (unsigned long long)d.ring_cap);
+    gr[GR_FIRST_LO] = (int32_t)(uint32_t)(head & 0xffffffffull);
+    gr[GR_FIRST_HI] = (int32_t)(uint32_t)(head >> 32);
     gr[GR_UID] = ti[TI_GAME_UID];
     memcpy(&gr[GR_SCORE_BITS], &sc, 4);
     atomic_add_u64(&E.counters[CT_GAMES], 1ull);

@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py — MCTS simulations/s (and self-play moves / games per s) of the self-play hot path.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                  # this framework on N B200s
+    python bench.py --impl reference --gpus 1 --steps 2 --warmup 1 # the reference CPU path (oracle port) on the host cores
+
+Workload (BASELINE.json configs[1]): 9x9 Go, 4096 concurrent games per GPU, 400 simulations/move,
+num_parallel 8, AlphaZeroNet 10 blocks x 128 filters (fc 128), random-init weights (seed 123, BN
+statistics randomised), synthetic = self-play from empty boards.  One *step* = 51 leaf batches
+(ticks) = (400+8)/8, i.e. about one move of every game: select -> network -> expand/backup ->
+move / re-root / recycle, all on the device.  A *simulation* is one root-visit increment
+(SURVEY.md 8d); the count comes from the engine's device counters.
+
+Timing: W untimed warm-up steps, then K steps bracketed by barrier + synchronize, CUDA events on
+the engine's own stream, max over ranks.  Every tick streams a ~2.5 GB working set (activations of
+up to 32768 leaves), far above the 126 MB L2, so no explicit L2 flush is needed ("inputs larger
+than L2").  `e2e` repeats the measurement through the public Python API with host buffers: weights
+go host->device every step (pinned source), finished games' (state, pi, z) samples and the counters
+come back device->host every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (game, board, games/GPU, sims, parallel, blocks, filters, fc, warm_up_steps, check_resign_after)
+    'go9_c2': ('go', 9, 4096, 400, 8, 10, 128, 128, 16, 40),
+    'gomoku13_c4': ('gomoku', 13, 1024, 200, 8, 6, 64, 64, 16, 0),
+    'go19_c5': ('go', 19, 128, 800, 8, 19, 256, 256, 30, 80),
+    'go9_tiny': ('go', 9, 256, 64, 8, 2, 64, 64, 8, 20),
+}
+
+
+def make_net(game, n, nb, nf, fc):
+    import torch
+
+    from alpha_zero_b200.network import AlphaZeroNet, randomize_batchnorm
+
+    torch.manual_seed(123)
+    a = n * n + (1 if game == 'go' else 0)
+    return randomize_batchnorm(AlphaZeroNet((17, n, n), a, nb, nf, fc, game == 'gomoku')).eval()
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx or None, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_worker(args):
+    """One reference-style actor: the oracle's restatement of play_and_record_one_game (pipeline.py:289-382),
+    single-threaded torch CPU net, until the time budget is spent.  Returns (simulations, moves, seconds)."""
+    seed, seconds, wl = args
+    os.environ['OMP_NUM_THREADS'] = '1'
+    os.environ['MKL_NUM_THREADS'] = '1'
+    import numpy as np
+    import torch
+
+    torch.set_num_threads(1)
+    from oracle import net as onet
+    from oracle.boards import GoBoard, GomokuBoard
+    from oracle.search import search
+
+    game, n, _, sims, par, nb, nf, fc, warm, _ = WORKLOADS[wl]
+    sd = make_net(game, n, nb, nf, fc).state_dict()
+    ev = onet.make_eval_func(sd, game == 'gomoku')
+    np.random.seed(seed)
+    env = GoBoard(n) if game == 'go' else GomokuBoard(n)
+    root, total, moves = None, 0.0, 0
+    t0 = time.time()
+    while time.time() - t0 < seconds:
+        if env.is_game_over():
+            env.reset()
+            root = None
+        before = float(root.tree.root_N) if root is not None else 0.0
+        mv, pi, rq, cq, root, child_N = search(env, ev, root, 19652.0, 1.25, sims, par, True, env.steps <= warm, False)
+        total += float(child_N.sum()) + 1.0 - before
+        moves += 1
+        env.step(mv)
+    return total, moves, time.time() - t0
+
+
+def run_cpu(wl, seconds, cores=None):
+    import multiprocessing as mp
+
+    cores = cores or os.cpu_count() or 1
+    ctx = mp.get_context('spawn')
+    with ctx.Pool(cores) as pool:
+        res = pool.map(cpu_worker, [(1 + i, seconds, wl) for i in range(cores)])
+    sims = sum(r[0] for r in res)
+    moves = sum(r[1] for r in res)
+    wall = max(r[2] for r in res)
+    return sims / wall, moves / wall, cores, wall
+
+
+def reference_arm(a):
+    """--impl reference: the reference's CPU self-play path (oracle port: numpy PUCT + Python board engine +
+    torch-CPU fp32 net, one single-threaded actor per host core like training_go.py:12,19,319) on the same workload."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    per_step = float(os.environ.get('AZ_REF_SECONDS', '12'))
+    for _ in range(a.warmup):
+        run_cpu(a.workload, 2.0)
+    vals, mv = [], []
+    t0 = time.time()
+    for _ in range(a.steps):
+        s, m, cores, wall = run_cpu(a.workload, per_step)
+        vals.append(s)
+        mv.append(m)
+    v = sum(vals) / len(vals)
+    game, n, G, sims, par, nb, nf, fc, _, _ = WORKLOADS[a.workload]
+    line = {
+        'impl': 'reference', 'metric': 'mcts_simulations_per_sec', 'value': v, 'unit': 'simulations/s', 'n_gpus': a.gpus, 'steps': a.steps,
+        'warmup': a.warmup, 'ms_per_step': 1000.0 * (time.time() - t0) / max(1, a.steps), 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'{a.workload}: {n}x{n} {game}, {sims} sims/move, num_parallel {par}, net {nb}x{nf} fc{fc}; one single-threaded actor process per host core'},
+        'moves_per_sec': sum(mv) / len(mv),
+        'cpu_baseline': {'value': v, 'unit': 'simulations/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'{cores} actor processes x {per_step:.0f} s of self-play per step (oracle port of the reference CPU path, torch {__import__("torch").__version__} CPU fp32)'},
+        'e2e': {'value': v, 'unit': 'simulations/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=4)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='go9_c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--games', type=int, default=0, help='override games per GPU')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    a = ap.parse_args()
+    if a.impl == 'reference':
+        return reference_arm(a)
+
+    import numpy as np
+    import torch
+
+    from alpha_zero_b200.engine import Engine
+
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    dist = None
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+
+    game, n, G, sims, par, nb, nf, fc, warm, chk = WORKLOADS[a.workload]
+    if a.games:
+        G = a.games
+    ticks = (sims + par + par - 1) // par  # leaf batches per move
+    net = make_net(game, n, nb, nf, fc)
+    sd = net.state_dict()
+    pinned = {k: v.pin_memory() for k, v in sd.items() if not k.endswith('num_batches_tracked')}
+    eng = Engine(game, n, num_games=G, max_simulations=sims, max_parallel=par, net=(nb, nf, fc), precision=a.precision, device=local, seed=1 + rank)
+    eng.set_weights(pinned)
+    stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device('cuda', local))
+    eng.selfplay_begin(sims, par, warm_up_steps=warm, check_resign_after_steps=chk, resign_threshold=-1.0, disable_resign_ratio=1.0)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather_samples(states, pis, zs):
+        """NCCL all-gather of the (state, pi, z) samples produced this step: fixed-capacity blocks + counts."""
+        if dist is None:
+            return len(zs)
+        cap = G * 2
+        k = min(len(zs), cap)
+        blk_s = torch.zeros((cap, eng.obs_bytes), dtype=torch.int8, device='cuda')
+        blk_p = torch.zeros((cap, eng.A), dtype=torch.float32, device='cuda')
+        blk_z = torch.zeros((cap + 1,), dtype=torch.float32, device='cuda')
+        if k:
+            blk_s[:k].copy_(torch.from_numpy(states[:k].reshape(k, -1)), non_blocking=True)
+            blk_p[:k].copy_(torch.from_numpy(pis[:k]), non_blocking=True)
+            blk_z[:k].copy_(torch.from_numpy(zs[:k]), non_blocking=True)
+        blk_z[cap] = float(k)
+        out_s = torch.empty((world * cap, eng.obs_bytes), dtype=torch.int8, device='cuda')
+        out_p = torch.empty((world * cap, eng.A), dtype=torch.float32, device='cuda')
+        out_z = torch.empty((world * (cap + 1),), dtype=torch.float32, device='cuda')
+        dist.all_gather_into_tensor(out_s, blk_s)
+        dist.all_gather_into_tensor(out_p, blk_p)
+        dist.all_gather_into_tensor(out_z, blk_z)
+        return int(out_z.view(world, cap + 1)[:, cap].sum().item())
+
+    # ---- warm-up --------------------------------------------------------------------------------
+    for _ in range(a.warmup):
+        eng.selfplay_tick(ticks)
+    eng.sync()
+    barrier()
+
+    # ---- device-resident measurement: `value` --------------------------------------------------
+    c0 = eng.counters()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        ev0.record(stream)
+        for _ in range(a.steps):
+            eng.selfplay_tick(ticks)
+        ev1.record(stream)
+        eng.sync()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    c1 = eng.counters()
+    tower_ms, tower_evals = eng.last_net_ms()
+
+    # ---- end to end through the public API with host buffers: `e2e` ----------------------------
+    d2h_bytes, gathered = 0, 0
+    barrier()
+    t0 = time.perf_counter()
+    ce0 = eng.counters()
+    for _ in range(a.steps):
+        eng.set_weights(pinned)  # host -> device: the step's network parameters (ckpt hot-swap, pipeline.py:232-239)
+        eng.selfplay_tick(ticks)
+        games, st, pis, zs = eng.drain_games()  # device -> host: finished games' (state, pi, z)
+        ce = eng.counters()  # device -> host: the step's result counters
+        d2h_bytes += st.nbytes + pis.nbytes + zs.nbytes + 12 * 8
+        gathered += gather_samples(st, pis, zs)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    ce1 = eng.counters()
+
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    ms_max = allmax(ms)
+    e2e_max = allmax(e2e_s)
+    d = {k: allsum(float(c1[k] - c0[k])) for k in ('simulations', 'evaluations', 'moves', 'games', 'descents', 'depth_sum')}
+    e2e_sims = allsum(float(ce1['simulations'] - ce0['simulations']))
+    launches = c1['kernel_launches'] - c0['kernel_launches']
+    errors = allsum(float(c1['errors']))
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        hw = n * n if game == 'go' else (n + 4) * (n + 4)
+        conv_flops_per_eval = 2.0 * hw * 9 * nf * nf  # one res-tower 3x3 conv layer, 2*MAC per leaf
+        n_conv = 1 + 2 * nb
+        launch_ms = tower_ms / n_conv if tower_ms > 0 else None
+        achieved = (tower_evals * conv_flops_per_eval / (launch_ms * 1e-3) / 1e12) if launch_ms else None
+        peak = peaks.get('bf16_tflops_sustained') if a.precision == 'bf16' else None
+        peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peak else 'fallback 1400 TF/s (of fallback)'
+        peak = peak or 1400.0
+        value = d['simulations'] / (ms_max * 1e-3)
+        line = {
+            'metric': 'mcts_simulations_per_sec', 'value': value, 'unit': 'simulations/s', 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
+            'ms_per_step': ms_max / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': a.precision if a.precision != 'fp32' else 'f32', 'data': 'synthetic',
+            'config': {'workload': f'{a.workload}: {n}x{n} {game}, {G} concurrent games per GPU, {sims} sims/move, num_parallel {par}, net {nb}x{nf} fc{fc} '
+                                   f'(random init seed 123); step = {ticks} leaf batches; working set >> L2 (no flush needed)',
+                       'games_per_gpu': G, 'parallelism': f'games sharded, {world} process(es), NCCL all-gather of samples only'},
+            'evals_per_sec': d['evaluations'] / (ms_max * 1e-3), 'moves_per_sec': d['moves'] / (ms_max * 1e-3),
+            'games_finished_in_window': d['games'], 'mean_leaf_depth': d['depth_sum'] / max(1.0, d['descents']), 'device_errors': errors,
+            'e2e': {'value': e2e_sims / e2e_max, 'unit': 'simulations/s', 'h2d_bytes_per_step': int(eng.weight_bytes),
+                    'd2h_bytes_per_step': int(d2h_bytes / max(1, a.steps)), 'samples_all_gathered': gathered},
+            'gpu_launches': int(launches),
+            'roofline': {'bound': 'tensor', 'kernel': 'k_conv_tc' if a.precision == 'bf16' else 'k_conv_f32', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+                         'frac': (achieved / peak) if achieved else None, 'traffic': None, 'peak_source': peak_src,
+                         'note': f'algorithmic 2*MAC of one 3x3 conv layer ({conv_flops_per_eval / 1e6:.1f} MFLOP/leaf) x {tower_evals} leaves / mean launch time over the '
+                                 f'{n_conv} tower launches of the last tick ({tower_ms:.3f} ms, CUDA events on the engine stream)'},
+            'clocks': clk.summary(),
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            secs = float(os.environ.get('AZ_CPU_SECONDS', '15'))
+            v, mvs, cores, wall = run_cpu(a.workload, secs)
+            line['cpu_baseline'] = {'value': v, 'unit': 'simulations/s', 'cores': cores, 'kind': 'port',
+                                    'sample': f'{cores} single-threaded actor processes x {secs:.0f} s of the same workload (oracle port, torch CPU fp32 net)'}
+        print(json.dumps(line))
+    eng.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

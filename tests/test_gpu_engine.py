@@ -1,0 +1,169 @@
+"""Parity of the CUDA engine (libaz_b200.so, through the C ABI) on a real B200.
+
+Board engines: bit-exact legal masks / boards / rewards / observations against the reference's own
+self-play corpus and unit-test sequences.  Search: visit counts identical to the reference traces under
+the shared deterministic evaluator.  Network: fp32 tower within 1e-4 of the reference forward; pi within
+1e-3 of the oracle search end to end.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import enginecheck
+
+pytestmark = pytest.mark.gpu
+GOLDEN = enginecheck.GOLDEN
+
+
+@pytest.fixture(scope='module')
+def cuda():
+    from alpha_zero_b200 import _lib
+
+    return _lib.load()
+
+
+@pytest.mark.parametrize('game', ['go9', 'gomoku13'])
+def test_env_corpus(cuda, game):
+    bad, n = enginecheck.replay_corpus(cuda, game, stride=int(os.environ.get('AZ_CORPUS_STRIDE', '3')), batch=256)
+    assert not bad, f'{len(bad)}/{n} games differ, first {bad[:5]}'
+
+
+@pytest.mark.parametrize('game', ['go9', 'gomoku13'])
+def test_env_observation_copy_export(cuda, game):
+    enginecheck.final_observations(cuda, game, count=24)
+
+
+def test_go19_unit(cuda):
+    enginecheck.go19_unit(cuda)
+
+
+def test_gomoku_unit(cuda):
+    enginecheck.gomoku_unit(cuda)
+
+
+@pytest.mark.parametrize('game', ['go9', 'gomoku13'])
+def test_mcts_traces(cuda, game):
+    assert enginecheck.mcts_traces(cuda, game) > 50
+
+
+def _net_case(tag):
+    from alpha_zero_b200.network import AlphaZeroNet, randomize_batchnorm
+
+    z = np.load(os.path.join(GOLDEN, 'net.npz'))
+    n, a, nb, nf, fc, gomoku = (int(v) for v in z[tag + '/cfg'])
+    torch.manual_seed(123)
+    net = randomize_batchnorm(AlphaZeroNet((17, n, n), a, nb, nf, fc, bool(gomoku))).eval()
+    return z, n, a, nb, nf, fc, bool(gomoku), net
+
+
+@pytest.mark.parametrize('tag', ['go9_small', 'go9_c2', 'gomoku13_small', 'gomoku13_c4'])
+def test_net_fp32_matches_reference(cuda, tag):
+    """fp32 CUDA tower vs AlphaZeroNet.forward of the reference (golden outputs), tolerance 1e-4 on pi and v."""
+    from alpha_zero_b200.engine import Engine
+
+    z, n, a, nb, nf, fc, gomoku, net = _net_case(tag)
+    eng = Engine('gomoku' if gomoku else 'go', n, num_games=4, max_simulations=8, max_parallel=2, net=(nb, nf, fc), precision='fp32')
+    eng.set_weights(net.state_dict())
+    pi, v = eng.net_forward(z[tag + '/x'])
+    np.testing.assert_allclose(pi, z[tag + '/pi'], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(v, z[tag + '/v'][:, 0], rtol=0, atol=1e-4)
+    eng.close()
+
+
+@pytest.mark.parametrize('tag', ['go9_c2', 'gomoku13_c4'])
+def test_net_bf16_matches_bf16_emulation(cuda, tag):
+    """tcgen05 tower (bf16 operands, f32 accumulation in TMEM) vs a torch restatement that rounds weights and stored
+    activations to bf16 at the same places (oracle/net.py:forward_bf16_emulated): pi within 1e-2, v within 2e-2.
+    The distance to the fp32 reference is rounding, not a bug: the same emulation sits equally far from it."""
+    from alpha_zero_b200.engine import Engine
+    from oracle import net as onet
+
+    z, n, a, nb, nf, fc, gomoku, net = _net_case(tag)
+    eng = Engine('gomoku' if gomoku else 'go', n, num_games=4, max_simulations=8, max_parallel=2, net=(nb, nf, fc), precision='bf16')
+    eng.set_weights(net.state_dict())
+    pi, v = eng.net_forward(z[tag + '/x'])
+    lg, ve = onet.forward_bf16_emulated(net.state_dict(), torch.from_numpy(z[tag + '/x']).float(), gomoku)
+    pe = torch.softmax(lg, dim=-1).numpy()
+    print(tag, 'kernel vs emulation', np.abs(pi - pe).max(), 'kernel vs fp32', np.abs(pi - z[tag + '/pi']).max(), 'emulation vs fp32', np.abs(pe - z[tag + '/pi']).max())
+    np.testing.assert_allclose(pi, pe, rtol=0, atol=1e-2)
+    np.testing.assert_allclose(v, ve.numpy()[:, 0], rtol=0, atol=2e-2)
+    assert np.abs(pi.sum(axis=1) - 1).max() < 1e-4
+    assert np.abs(pi - z[tag + '/pi']).max() < 2.5 * max(np.abs(pe - z[tag + '/pi']).max(), 1e-2)
+    eng.close()
+
+
+@pytest.mark.parametrize('game', ['go9', 'gomoku13'])
+def test_search_with_cuda_net_vs_oracle(cuda, game):
+    """Fixed-seed positions: pi from the CUDA search + CUDA fp32 net vs the oracle search + torch fp32 net: within 1e-3;
+    legal masks bit-exact; z (game result) identical after playing the game out deterministically."""
+    from alpha_zero_b200.engine import Engine
+    from oracle import net as onet
+    from oracle.boards import GoBoard, GomokuBoard
+    from oracle.search import search
+
+    tag = f'{game}_small'
+    z, n, a, nb, nf, fc, gomoku, net = _net_case(tag)
+    sd = net.state_dict()
+    eng = Engine('gomoku' if gomoku else 'go', n, num_games=2, max_simulations=128, max_parallel=8, net=(nb, nf, fc), precision='fp32',
+                 max_steps=60 if not gomoku else 0)
+    eng.set_weights(sd)
+    ev = onet.make_eval_func(sd, gomoku)
+    env = GomokuBoard(n, 5, 8) if gomoku else GoBoard(n, 7.5, 8, 60)
+    root, reuse, worst, plies, exact = None, False, 0.0, 0, 0
+    done = False
+    while not done and plies < 60:
+        eng.search_begin([0], [int(reuse)], 19652.0, 1.25, 96, 8, False, plies < 8, True)
+        eng.search_run()
+        res = eng.search_result(0)
+        mv, pi, rq, cq, root, child_N = search(env, ev, root, 19652.0, 1.25, 96, 8, False, plies < 8, True)
+        worst = max(worst, float(np.abs(res['pi'] - pi).max()))
+        exact += int(np.array_equal(res['child_N'], child_N))
+        assert res['argmax'] == mv
+        _, reuse = eng.search_commit(0, mv)
+        r, d = eng.env_step([0], [mv])
+        _, r2, done, _ = env.step(mv)
+        assert r[0] == r2 and bool(d[0]) == done
+        np.testing.assert_array_equal(eng.env_legal(0), np.asarray(env.legal_actions).astype(np.uint8))
+        plies += 1
+    assert worst < 1e-3, worst
+    assert exact >= plies - 2, (exact, plies)
+    eng.close()
+
+
+def test_selfplay_device_loop(cuda):
+    """Device-resident self-play: finished games come back with consistent (state, pi, z) samples."""
+    from alpha_zero_b200.engine import Engine
+
+    z, n, a, nb, nf, fc, gomoku, net = _net_case('go9_small')
+    eng = Engine('go', 9, num_games=64, max_simulations=32, max_parallel=4, net=(nb, nf, fc), precision='fp32', max_steps=30, seed=5)
+    eng.set_weights(net.state_dict())
+    eng.selfplay_begin(24, 4, warm_up_steps=4, check_resign_after_steps=8, resign_threshold=-0.9, disable_resign_ratio=0.5)
+    total_games = 0
+    for rnd in range(40):
+        eng.selfplay_tick(10)
+        games, states, pis, zs = eng.drain_games()
+        total_games += len(games)
+        assert len(states) == sum(g['game_length'] for g in games)
+        if len(games):
+            np.testing.assert_allclose(pis.sum(axis=1), 1.0, atol=1e-5)
+        _check_games(games, states, zs)
+    c = eng.counters()
+    assert c['errors'] == 0 and c['games'] > 0 and c['moves'] > 64 and c['ring_dropped'] == 0, c
+    assert total_games == c['games']
+    eng.close()
+
+
+def _check_games(games, states, zs):
+    for g in games:
+        s0, ln = g['first_sample'], g['game_length']
+        assert np.all(states[s0, :16] == 0) and np.all(states[s0, 16] == 1)  # empty board, black to play
+        colour = states[s0:s0 + ln, 16, 0, 0]
+        assert np.all(colour[::2] == 1) and np.all(colour[1::2] == 0)
+        zz = zs[s0:s0 + ln]
+        if g['winner'] == 0:
+            assert np.all(zz == 0)
+        else:
+            black_z = 1.0 if g['winner'] == 1 else -1.0
+            np.testing.assert_array_equal(zz, np.where(colour == 1, black_z, -black_z))

@@ -1,0 +1,21 @@
+import os, sys, numpy as np, torch
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, 'tests')
+from alpha_zero_b200.engine import Engine
+from alpha_zero_b200.network import AlphaZeroNet, randomize_batchnorm
+z = np.load('tests/golden/net.npz')
+def case(tag, prec):
+    n, a, nb, nf, fc, gomoku = (int(v) for v in z[tag + '/cfg'])
+    torch.manual_seed(123)
+    net = randomize_batchnorm(AlphaZeroNet((17, n, n), a, nb, nf, fc, bool(gomoku))).eval()
+    try:
+        eng = Engine('gomoku' if gomoku else 'go', n, num_games=4, max_simulations=8, max_parallel=2, net=(nb, nf, fc), precision=prec)
+        eng.set_weights(net.state_dict())
+        pi, v = eng.net_forward(z[tag + '/x'])
+        print(tag, prec, 'max|dpi|', float(np.abs(pi - z[tag + '/pi']).max()), 'max|dv|', float(np.abs(v - z[tag + '/v'][:, 0]).max()), flush=True)
+        eng.close()
+    except Exception as ex:
+        print(tag, prec, 'ERROR', repr(ex), flush=True)
+which = sys.argv[1:] or ['fp32', 'bf16']
+for prec in which:
+    for tag in (['go9_small', 'gomoku13_small', 'go9_c2', 'gomoku13_c4'] if prec == 'fp32' else ['gomoku13_c4', 'go9_c2']):
+        case(tag, prec)
