@@ -145,9 +145,11 @@ extern "C" int az_create(const az_config* cfg, az_engine** out) {
   E.g_obs = dev_alloc<int8_t>(e, G * d.max_len * d.obs_bytes);
   E.g_pi = dev_alloc<float>(e, G * d.max_len * d.A);
   E.g_to_play = dev_alloc<int8_t>(e, G * d.max_len);
+  E.g_move = dev_alloc<int16_t>(e, G * d.max_len);
   E.r_obs = dev_alloc<int8_t>(e, (size_t)d.ring_cap * d.obs_bytes);
   E.r_pi = dev_alloc<float>(e, (size_t)d.ring_cap * d.A);
   E.r_z = dev_alloc<float>(e, d.ring_cap);
+  E.r_move = dev_alloc<int16_t>(e, d.ring_cap);
   E.games_ring = dev_alloc<int32_t>(e, (size_t)AZ_GAMES_RING * GR_INTS);
   E.counters = dev_alloc<unsigned long long>(e, CT_COUNT);
   e->d_slots = dev_alloc<int32_t>(e, G);
@@ -550,6 +552,17 @@ extern "C" int az_selfplay_begin(az_engine* e, const az_selfplay_params* p) {
   return rt_sync(e->rt);
 }
 
+extern "C" int az_selfplay_update(az_engine* e, const az_selfplay_params* p) {
+  if (!e || !p) return az_fail(AZ_ERR_BAD_ARG, "null argument");
+  if (!e->selfplay) return az_fail(AZ_ERR_STATE, "az_selfplay_update: call az_selfplay_begin first");
+  AzSearchCfg& s = e->E.s;  // games in flight keep running; only the per-move / per-new-game policy knobs change
+  s.warm_up_steps = p->warm_up_steps;
+  s.check_resign_after = p->check_resign_after_steps;
+  s.resign_threshold = p->resign_threshold;
+  s.disable_resign_ratio = p->disable_resign_ratio;
+  return AZ_OK;
+}
+
 extern "C" int az_selfplay_tick(az_engine* e, int32_t n_ticks) {
   if (!e) return az_fail(AZ_ERR_BAD_ARG, "null engine");
   if (!e->selfplay) return az_fail(AZ_ERR_STATE, "az_selfplay_tick: call az_selfplay_begin first");
@@ -600,7 +613,7 @@ extern "C" int az_get_counters(az_engine* e, az_counters* out) {
 }
 
 extern "C" int az_drain_games(az_engine* e, az_game_record* records, int32_t max_games, int32_t* n_games, int8_t* states,
-                              float* pis, float* values, int32_t max_samples, int32_t* n_samples) {
+                              float* pis, float* values, int16_t* moves, int32_t max_samples, int32_t* n_samples) {
   if (!e || !n_games || !n_samples) return az_fail(AZ_ERR_BAD_ARG, "null argument");
   const AzDims& d = e->E.d;
   int rc = rt_sync(e->rt);
@@ -650,6 +663,10 @@ extern "C" int az_drain_games(az_engine* e, az_game_record* records, int32_t max
     if (values) {
       rt_d2h(e->rt, values + ns, e->E.r_z + s0, n1 * sizeof(float));
       if (n2) rt_d2h(e->rt, values + ns + n1, e->E.r_z, n2 * sizeof(float));
+    }
+    if (moves) {
+      rt_d2h(e->rt, moves + ns, e->E.r_move + s0, n1 * sizeof(int16_t));
+      if (n2) rt_d2h(e->rt, moves + ns + n1, e->E.r_move, n2 * sizeof(int16_t));
     }
     ns += len;
     ng++;

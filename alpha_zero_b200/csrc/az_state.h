@@ -121,10 +121,12 @@ struct AzState {
   int8_t* g_obs;        // [G][max_len][obs_bytes]
   float* g_pi;          // [G][max_len][A]
   int8_t* g_to_play;    // [G][max_len]
+  int16_t* g_move;      // [G][max_len] move played at each ply (-1 resign)
   // finished-sample ring + finished-game ring
   int8_t* r_obs;
   float* r_pi;
   float* r_z;
+  int16_t* r_move;
   int32_t* games_ring;  // [ring_games][GR_INTS]
   unsigned long long* counters;  // see CT_*
 };

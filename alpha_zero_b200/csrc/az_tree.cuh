@@ -494,6 +494,7 @@ AZ_DEV void game_advance(const AzState& E, int g, Sim& S) {
     W_LANE0 if (ti[TI_MARKED] == 0) ti[TI_MARKED] = ei[EI_TO_PLAY];
     if (!ti[TI_RESIGN_DISABLED]) play = -1;
   }
+  W_LANE0 if (ply < d.max_len) E.g_move[(size_t)g * d.max_len + ply] = (int16_t)play;
   w_sync();
   const StepOut o = env_step(E, g, S, play);
   W_LANE0 {
@@ -538,6 +539,7 @@ AZ_DEV void game_advance(const AzState& E, int g, Sim& S) {
       float z = 0.f;
       if (reward != 0.f) z = (E.g_to_play[(size_t)g * d.max_len + i] == last_player) ? reward : -reward;
       E.r_z[slot] = z;
+      E.r_move[slot] = E.g_move[(size_t)g * d.max_len + i];
     }
   }
   W_LANE0 {

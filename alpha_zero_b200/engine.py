@@ -177,6 +177,10 @@ class Engine:
                               int(warm_up_steps), int(check_resign_after_steps), float(resign_threshold), float(disable_resign_ratio))
         self.b.check(self.b.dll.az_selfplay_begin(self.h, C.byref(sp)))
 
+    def selfplay_update(self, warm_up_steps, check_resign_after_steps, resign_threshold, disable_resign_ratio):
+        sp = AzSelfplayParams(AzSearchParams(0.0, 0.0, 1, 1, 0, 0), int(warm_up_steps), int(check_resign_after_steps), float(resign_threshold), float(disable_resign_ratio))
+        self.b.check(self.b.dll.az_selfplay_update(self.h, C.byref(sp)))
+
     def selfplay_tick(self, n=1):
         self.b.check(self.b.dll.az_selfplay_tick(self.h, int(n)))
 
@@ -194,9 +198,11 @@ class Engine:
         st = np.empty((max_samples, self.obs_bytes), dtype=np.int8)
         pis = np.empty((max_samples, self.A), dtype=np.float32)
         z = np.empty(max_samples, dtype=np.float32)
+        mv = np.empty(max_samples, dtype=np.int16)
         ng, ns = C.c_int32(), C.c_int32()
         self.b.check(self.b.dll.az_drain_games(self.h, recs, max_games, C.byref(ng), as_ptr(st, C.c_int8), as_ptr(pis, C.c_float),
-                                               as_ptr(z, C.c_float), max_samples, C.byref(ns)))
+                                               as_ptr(z, C.c_float), as_ptr(mv, C.c_int16), max_samples, C.byref(ns)))
+        self.last_moves = mv[: ns.value]
         games = [{k: getattr(recs[i], k) for k, _ in AzGameRecord._fields_} for i in range(ng.value)]
         n = ns.value
         return games, st[:n].reshape(n, self.planes, self.N, self.N), pis[:n], z[:n]

@@ -170,12 +170,16 @@ int az_search_run(az_engine* e);
  * (select -> network -> apply -> advance) without host synchronisation. */
 int az_selfplay_begin(az_engine* e, const az_selfplay_params* p);
 int az_selfplay_tick(az_engine* e, int32_t n_ticks);
+/* Change warm-up / resignation knobs of the running loop without resetting the games
+ * (var_resign_threshold is re-read before every game, core/pipeline.py:241-246). */
+int az_selfplay_update(az_engine* e, const az_selfplay_params* p);
 int az_sync(az_engine* e);
 int az_get_counters(az_engine* e, az_counters* out);
 /* Drain finished games: up to max_games records and their samples, oldest first.
- * states int8 [*, obs_bytes], pis float32 [*, A], values float32 [*] (z, core/pipeline.py:349-354). */
+ * states int8 [*, obs_bytes], pis float32 [*, A], values float32 [*] (z, core/pipeline.py:349-354),
+ * moves int16 [*] (the move played at each ply, -1 = resign: env.history for to_sgf, envs/go.py:202). */
 int az_drain_games(az_engine* e, az_game_record* records, int32_t max_games, int32_t* n_games, int8_t* states,
-                   float* pis, float* values, int32_t max_samples, int32_t* n_samples);
+                   float* pis, float* values, int16_t* moves, int32_t max_samples, int32_t* n_samples);
 /* Device pointers of the last drained-but-not-copied sample block for NCCL all-gather by the caller. */
 int az_sample_ring_device(az_engine* e, void** states, void** pis, void** values, int64_t* head, int32_t* capacity);
 /* The CUDA stream every engine kernel is launched on (bench.py times on it with its own events). */
