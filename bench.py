@@ -224,23 +224,10 @@ def main():
         """NCCL all-gather of the (state, pi, z) samples produced this step: fixed-capacity blocks + counts."""
         if dist is None:
             return len(zs)
-        cap = G * 2
-        k = min(len(zs), cap)
-        blk_s = torch.zeros((cap, eng.obs_bytes), dtype=torch.int8, device='cuda')
-        blk_p = torch.zeros((cap, eng.A), dtype=torch.float32, device='cuda')
-        blk_z = torch.zeros((cap + 1,), dtype=torch.float32, device='cuda')
-        if k:
-            blk_s[:k].copy_(torch.from_numpy(states[:k].reshape(k, -1)), non_blocking=True)
-            blk_p[:k].copy_(torch.from_numpy(pis[:k]), non_blocking=True)
-            blk_z[:k].copy_(torch.from_numpy(zs[:k]), non_blocking=True)
-        blk_z[cap] = float(k)
-        out_s = torch.empty((world * cap, eng.obs_bytes), dtype=torch.int8, device='cuda')
-        out_p = torch.empty((world * cap, eng.A), dtype=torch.float32, device='cuda')
-        out_z = torch.empty((world * (cap + 1),), dtype=torch.float32, device='cuda')
-        dist.all_gather_into_tensor(out_s, blk_s)
-        dist.all_gather_into_tensor(out_p, blk_p)
-        dist.all_gather_into_tensor(out_z, blk_z)
-        return int(out_z.view(world, cap + 1)[:, cap].sum().item())
+        from alpha_zero_b200.gather import all_gather_samples
+
+        S, P, Z, _ = all_gather_samples(states, pis, zs, capacity=G * 2, device=f'cuda:{local}')
+        return len(Z)
 
     # ---- warm-up --------------------------------------------------------------------------------
     for _ in range(a.warmup):
