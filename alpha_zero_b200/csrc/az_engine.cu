@@ -103,7 +103,14 @@ extern "C" int az_create(const az_config* cfg, az_engine** out) {
   d.pass_move = cfg->game == AZ_GAME_GO ? d.nc : -1;
   d.table_len = d.cap + 64;
   d.max_len = (cfg->game == AZ_GAME_GO ? d.max_steps : d.nc) + 1;
-  d.ring_cap = cfg->sample_ring > 0 ? cfg->sample_ring : std::max(4 * d.max_len, 2 * d.G * 8);
+  {
+    // default: room for every slot finishing a maximum-length game between two drains, twice over (bounded to 8 GB)
+    const double per_sample = (double)d.obs_bytes + 4.0 * d.A + 6.0;
+    double want = 2.0 * (double)d.G * (double)d.max_len;
+    const double cap_bytes = 8.0 * 1024 * 1024 * 1024;
+    if (want * per_sample > cap_bytes) want = std::max((double)d.G * d.max_len, cap_bytes / per_sample);
+    d.ring_cap = cfg->sample_ring > 0 ? cfg->sample_ring : (int)std::min(want, 2.0e9);
+  }
   e->cfg.max_steps = d.max_steps;
   e->cfg.sample_ring = d.ring_cap;
   AzState& E = e->E;

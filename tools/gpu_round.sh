@@ -3,7 +3,7 @@
 set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv
-python -m pytest tests -m gpu -q -x -s 2>&1 | tail -25 | tee gpurun_out/pytest_gpu.log
+python -m pytest tests -m gpu -q 2>&1 | tail -${TAIL:-25} | tee gpurun_out/pytest_gpu.log
 python __graft_entry__.py --smoke 2>&1 | tail -5 | tee gpurun_out/smoke.log
 python bench.py --steps ${STEPS:-3} --warmup 3 2>gpurun_out/bench.err | tee gpurun_out/bench.json
 tail -5 gpurun_out/bench.err
