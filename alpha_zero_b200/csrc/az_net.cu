@@ -123,7 +123,7 @@ AzNet* aznet_create(const AzDims& d, const az_config& cfg, AzRt& rt, int max_lea
   if (n->C % 64 != 0 && n->precision == AZ_NET_BF16) { err = "bf16 tower needs num_filters to be a multiple of 64"; delete n; return nullptr; }
   if (n->C % 16 != 0 || n->C < 16) { err = "num_filters must be a multiple of 16"; delete n; return nullptr; }
   if (d.planes > g.cin_pad) { err = "observation has more than 32 planes"; delete n; return nullptr; }
-  n->rows_total = (size_t)max_leaves * g.RP + 2 * (size_t)g.guard + 128;
+  n->rows_total = (size_t)max_leaves * g.RP + 2 * (size_t)g.guard + 512;
   const size_t esz = n->precision == AZ_NET_BF16 ? 2 : 4;
   n->act_in = rt_alloc(n->rows_total * g.cin_pad * esz);
   n->act_x = rt_alloc(n->rows_total * n->C * esz);
@@ -260,8 +260,6 @@ int aznet_forward(AzNet* n, AzRt& rt, const int8_t* obs_base, const int32_t* row
   if (!n || !n->ready) return AZ_ERR_STATE;
   if (max_rows > n->max_leaves) max_rows = n->max_leaves;
   const NetGeom& g = n->g;
-  const int HW = g.Hc * g.Hc;
-  const size_t head_smem = (size_t)(3 * HW + n->fc + n->A) * sizeof(float);
   if (n->precision == AZ_NET_BF16) return aznet_tc_forward(n, rt, obs_base, row_list, n_rows_dev, max_rows, priors_base, values_base, pri_stride);
   {
     long long work = (long long)max_rows * g.nc;
@@ -280,7 +278,7 @@ int aznet_forward(AzNet* n, AzRt& rt, const int8_t* obs_base, const int32_t* row
     k_conv_f32<<<grid, 256, 0, rt.stream>>>(MID, n->conv_w[2 + 2 * b], n->conv_b[2 + 2 * b], X, X, n_rows_dev, g, n->C, n->C, 1);
     rt.launches += 2;
   }
-  k_heads<float><<<max_rows, 128, head_smem, rt.stream>>>(X, row_list, n_rows_dev, n->hp, g, n->C, n->A, n->fc, priors_base, values_base, pri_stride);
+  launch_heads<float>(rt.stream, X, row_list, n_rows_dev, n->hp, g, n->C, n->A, n->fc, priors_base, values_base, pri_stride, max_rows);
   rt.launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_az_error = std::string("network launch: ") + cudaGetErrorString(e); return AZ_ERR_CUDA; }

@@ -15,35 +15,49 @@ static __global__ void k_net_input(const int8_t* __restrict__ obs_base, const in
     const int y = c / g.n, x = c - y * g.n;
     const size_t src = (size_t)(row_list ? row_list[leaf] : leaf) * g.obs_bytes;
     T* dst = act + ((size_t)g.guard + (size_t)leaf * g.RP + (size_t)(y + g.off) * g.Wr + (x + g.off)) * g.cin_pad;
-#pragma unroll 4
-    for (int p = 0; p < g.planes; ++p) dst[p] = (T)(float)obs_base[src + (size_t)p * g.nc + c];
-    for (int p = g.planes; p < g.cin_pad; ++p) dst[p] = (T)0.f;
+    // one feature row = cin_pad channels = 128 bytes: assemble the 32 leading channels in registers, store 16 bytes at a time
+    __align__(16) T vals[32];
+#pragma unroll
+    for (int p = 0; p < 32; ++p) vals[p] = (T)((p < g.planes) ? (float)obs_base[src + (size_t)p * g.nc + c] : 0.f);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    const uint4* s4 = reinterpret_cast<const uint4*>(vals);
+    constexpr int kData = (int)(32 * sizeof(T) / 16);
+    const int nvec = (int)(g.cin_pad * sizeof(T) / 16);
+#pragma unroll
+    for (int k = 0; k < kData; ++k) d4[k] = s4[k];
+    for (int k = kData; k < nvec; ++k) d4[k] = make_uint4(0, 0, 0, 0);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// heads (network.py:127-156) + softmax over ALL actions (pipeline.py:108): one CTA per leaf.
+// heads (network.py:127-156) + softmax over ALL actions (pipeline.py:108).
+// One CTA (8 warps) handles LPB leaves so that every FC weight row fetched from L2 is used LPB times.
+//   phase 1  1x1 policy (2 ch) / value (1 ch) convs + folded BN + ReLU: one warp per board position
+//   phase 2  policy FC (A rows) and value FC1 (fc rows): one warp per output row, LPB accumulators
+//   phase 3  softmax / value FC2 + tanh: one warp per leaf
 template <typename T>
-static __global__ void __launch_bounds__(128) k_heads(const T* __restrict__ feat, const int32_t* __restrict__ row_list,
-                                               const int32_t* __restrict__ n_rows, HeadParams hp, NetGeom g, int C, int A,
-                                               int fc, float* __restrict__ priors, float* __restrict__ values, int pri_stride) {
-  const int leaf = blockIdx.x;
-  if (leaf >= *n_rows) return;
+__device__ __forceinline__ float head_ld(const T* p) { return (float)*p; }
+
+template <typename T, int LPB>
+static __global__ void __launch_bounds__(256) k_heads(const T* __restrict__ feat, const int32_t* __restrict__ row_list,
+                                                      const int32_t* __restrict__ n_rows, HeadParams hp, NetGeom g, int C, int A,
+                                                      int fc, float* __restrict__ priors, float* __restrict__ values, int pri_stride) {
+  const int n = *n_rows;
+  const int leaf0 = blockIdx.x * LPB;
+  if (leaf0 >= n) return;
+  const int nl = min(LPB, n - leaf0);
   extern __shared__ float sh[];
   const int HW = g.Hc * g.Hc;
-  float* s_pol = sh;                 // [2*HW]  flatten order (c, y, x)
-  float* s_val = s_pol + 2 * HW;     // [HW]
-  float* s_fc = s_val + HW;          // [fc]
-  float* s_log = s_fc + fc;          // [A]
-  __shared__ float s_red[4];
+  const int per = 3 * HW + fc + A;       // floats per leaf: pol[2*HW] | val[HW] | fc1[fc] | logits[A]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // 1x1 convs: one warp per position, lanes split the channels
-  for (int pos = warp; pos < HW; pos += 4) {
+  // ---- phase 1
+  for (int idx = warp; idx < nl * HW; idx += 8) {
+    const int l = idx / HW, pos = idx - l * HW;
     const int y = pos / g.Hc, x = pos - y * g.Hc;
-    const T* f = feat + ((size_t)g.guard + (size_t)leaf * g.RP + (size_t)y * g.Wr + x) * C;
+    const T* f = feat + ((size_t)g.guard + (size_t)(leaf0 + l) * g.RP + (size_t)y * g.Wr + x) * C;
     float p0 = 0.f, p1 = 0.f, v0 = 0.f;
     for (int c = lane; c < C; c += 32) {
-      const float a = (float)f[c];
+      const float a = head_ld(f + c);
       p0 = fmaf(a, hp.pol_w[c], p0);
       p1 = fmaf(a, hp.pol_w[C + c], p1);
       v0 = fmaf(a, hp.val_w[c], v0);
@@ -54,54 +68,76 @@ static __global__ void __launch_bounds__(128) k_heads(const T* __restrict__ feat
       v0 += __shfl_xor_sync(0xffffffffu, v0, o);
     }
     if (lane == 0) {
-      s_pol[pos] = fmaxf(p0 + hp.pol_b[0], 0.f);
-      s_pol[HW + pos] = fmaxf(p1 + hp.pol_b[1], 0.f);
-      s_val[pos] = fmaxf(v0 + hp.val_b[0], 0.f);
+      float* s = sh + (size_t)l * per;
+      s[pos] = fmaxf(p0 + hp.pol_b[0], 0.f);
+      s[HW + pos] = fmaxf(p1 + hp.pol_b[1], 0.f);
+      s[2 * HW + pos] = fmaxf(v0 + hp.val_b[0], 0.f);
     }
   }
   __syncthreads();
-  // policy FC and value FC1: one warp per output row, coalesced weight reads
-  for (int a = warp; a < A + fc; a += 4) {
-    float acc = 0.f;
-    if (a < A) {
-      const float* wr = hp.pol_fc_w + (size_t)a * 2 * HW;
-      for (int k = lane; k < 2 * HW; k += 32) acc = fmaf(s_pol[k], wr[k], acc);
-    } else {
-      const float* wr = hp.val_fc1_w + (size_t)(a - A) * HW;
-      for (int k = lane; k < HW; k += 32) acc = fmaf(s_val[k], wr[k], acc);
+  // ---- phase 2
+  for (int a = warp; a < A + fc; a += 8) {
+    float acc[LPB];
+#pragma unroll
+    for (int l = 0; l < LPB; ++l) acc[l] = 0.f;
+    const bool is_pol = a < A;
+    const float* wr = is_pol ? hp.pol_fc_w + (size_t)a * 2 * HW : hp.val_fc1_w + (size_t)(a - A) * HW;
+    const int klen = is_pol ? 2 * HW : HW;
+    const int soff = is_pol ? 0 : 2 * HW;
+    for (int k = lane; k < klen; k += 32) {
+      const float w = wr[k];
+#pragma unroll
+      for (int l = 0; l < LPB; ++l) acc[l] = fmaf(sh[(size_t)l * per + soff + k], w, acc[l]);
     }
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+#pragma unroll
+    for (int l = 0; l < LPB; ++l)
+      for (int o = 16; o > 0; o >>= 1) acc[l] += __shfl_xor_sync(0xffffffffu, acc[l], o);
     if (lane == 0) {
-      if (a < A) s_log[a] = acc + hp.pol_fc_b[a];
-      else s_fc[a - A] = fmaxf(acc + hp.val_fc1_b[a - A], 0.f);
+      const float bv = is_pol ? hp.pol_fc_b[a] : hp.val_fc1_b[a - A];
+#pragma unroll
+      for (int l = 0; l < LPB; ++l) {
+        if (l < nl) {
+          float* s = sh + (size_t)l * per;
+          if (is_pol) s[3 * HW + fc + a] = acc[l] + bv;
+          else s[3 * HW + (a - A)] = fmaxf(acc[l] + bv, 0.f);
+        }
+      }
     }
   }
   __syncthreads();
-  // softmax
-  float mx = -INFINITY;
-  for (int a = tid; a < A; a += 128) mx = fmaxf(mx, s_log[a]);
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if (lane == 0) s_red[warp] = mx;
-  __syncthreads();
-  mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
-  __syncthreads();
-  float sum = 0.f;
-  for (int a = tid; a < A; a += 128) {
-    const float e = expf(s_log[a] - mx);
-    s_log[a] = e;
-    sum += e;
-  }
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  if (lane == 0) s_red[warp] = sum;
-  __syncthreads();
-  sum = s_red[0] + s_red[1] + s_red[2] + s_red[3];
-  const size_t orow = (size_t)(row_list ? row_list[leaf] : leaf);
-  for (int a = tid; a < A; a += 128) priors[orow * pri_stride + a] = s_log[a] / sum;
-  if (warp == 0) {
+  // ---- phase 3
+  for (int l = warp; l < nl; l += 8) {
+    float* s = sh + (size_t)l * per;
+    float* lg = s + 3 * HW + fc;
+    float mx = -INFINITY;
+    for (int a = lane; a < A; a += 32) mx = fmaxf(mx, lg[a]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int a = lane; a < A; a += 32) {
+      const float e = expf(lg[a] - mx);
+      lg[a] = e;
+      sum += e;
+    }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const size_t orow = (size_t)(row_list ? row_list[leaf0 + l] : leaf0 + l);
+    for (int a = lane; a < A; a += 32) priors[orow * pri_stride + a] = lg[a] / sum;
     float acc = 0.f;
-    for (int k = lane; k < fc; k += 32) acc = fmaf(s_fc[k], hp.val_fc2_w[k], acc);
+    for (int k = lane; k < fc; k += 32) acc = fmaf(s[3 * HW + k], hp.val_fc2_w[k], acc);
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) values[orow] = tanhf(acc + hp.val_fc2_b[0]);
   }
 }
 
+// host helper: launch the heads with the largest LPB whose shared memory fits the default 48 KB
+template <typename T>
+static inline void launch_heads(cudaStream_t stream, const T* feat, const int32_t* row_list, const int32_t* n_rows, const HeadParams& hp,
+                                const NetGeom& g, int C, int A, int fc, float* priors, float* values, int pri_stride, int max_rows) {
+  const int HW = g.Hc * g.Hc;
+  const size_t per = (size_t)(3 * HW + fc + A) * sizeof(float);
+  if (per * 8 <= 48 * 1024)
+    k_heads<T, 8><<<(max_rows + 7) / 8, 256, per * 8, stream>>>(feat, row_list, n_rows, hp, g, C, A, fc, priors, values, pri_stride);
+  else if (per * 4 <= 48 * 1024)
+    k_heads<T, 4><<<(max_rows + 3) / 4, 256, per * 4, stream>>>(feat, row_list, n_rows, hp, g, C, A, fc, priors, values, pri_stride);
+  else
+    k_heads<T, 1><<<max_rows, 256, per, stream>>>(feat, row_list, n_rows, hp, g, C, A, fc, priors, values, pri_stride);
+}

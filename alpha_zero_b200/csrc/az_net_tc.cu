@@ -28,6 +28,10 @@
 
 struct AzNetTc {
   CUtensorMap map_in, map_x, map_mid;
+  CUtensorMap hmap_in[2], hmap_x[2], hmap_mid[2];  // halo kernel: [0] 256-row box, [1] tail box (AR-256 rows)
+  int mode = 0;            // AZ_TC_MODE: 0 = one TMA box per tap, 1/2 = halo tile + row-shifted descriptors (base-offset variants)
+  int halo = 0, AR = 0;
+  size_t halo_smem = 0;
   std::vector<CUtensorMap> map_w;
   std::vector<__nv_bfloat16*> w_dev;
   int cin0 = 64;
@@ -243,6 +247,249 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Halo variant (default for <= 128 filters): the activation tile (256 output rows + one board row + 1 of
+// halo on each side, all input channels) is loaded ONCE per tile; the nine taps are row-shifted views of
+// it, addressed by moving the UMMA shared-memory descriptor's start address by whole 128-byte rows (the
+// hardware applies the 128B swizzle on absolute shared-memory address bits, so an unaligned start needs
+// no base offset — measured on B200: base_offset = 0 is exact, (addr>>7)&7 is wrong).  Weights stream
+// through a 3-stage ring, each 16 KB chunk feeding 8 MMAs (two 128-row halves x four K=16 steps).
+// L2->smem operand traffic per 128 output rows: ~180 KB instead of 576 KB for the per-tap kernel.
+// Epilogue: 8 warps (two per TMEM lane quarter, splitting the columns); residual rows are fetched and
+// results written back through a per-warp shared-memory staging tile so that every global access is a
+// full 128-byte line (the naive one-row-per-lane pattern issues 32 partial sectors per instruction).
+#define H_BSTAGES 3
+#define H_EPI_WARPS 8
+#define H_MMA_WARPS 2
+#define H_THREADS (32 * (1 + H_MMA_WARPS + H_EPI_WARPS))
+
+struct HaloLayer {
+  int cin, cout, relu, has_res;
+  int Wr, Hc, RP, guard;
+  int halo, AR;   // halo rows on each side; rows of the staged tile (multiple of 8)
+  int bo_mode;    // experiment switch: 1 puts (start >> 7) & 7 into the descriptor's base-offset field (wrong on B200)
+};
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+__global__ void __launch_bounds__(H_THREADS, 1)
+k_conv_tc_halo(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b,
+               const float* __restrict__ bias, const __nv_bfloat16* res, __nv_bfloat16* out, const int32_t* __restrict__ n_rows, HaloLayer L) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int kc = L.cin / TC_BK;
+  const uint32_t a_chunk = (uint32_t)L.AR * 128u, a_buf = (uint32_t)kc * a_chunk;
+  const uint32_t a_buf_max = 2u * a_chunk;  // buffers are carved for cin = 128
+  const uint32_t b_bytes = (uint32_t)L.cout * TC_BK * 2;
+  const int cw = L.cout / 2;                 // columns per epilogue warp
+  const uint32_t srow = (uint32_t)cw * 2 + 16;  // staging row pitch (bytes), +16 keeps 16-byte accesses conflict-free
+  unsigned char* smA = smem;
+  unsigned char* smB = smem + 2 * (size_t)a_buf_max;
+  unsigned char* smS = smB + (size_t)H_BSTAGES * b_bytes;
+  float* s_bias = (float*)(smS + (size_t)H_EPI_WARPS * 32 * srow);
+  uint64_t* a_full = (uint64_t*)(s_bias + L.cout);
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* b_full = a_empty + 2;
+  uint64_t* b_empty = b_full + H_BSTAGES;
+  uint64_t* tfull_bar = b_empty + H_BSTAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long M = (long long)(*n_rows) * L.RP;
+  const int num_tiles = (int)((M + 255) / 256);
+  uint32_t tmem_cols = 4 * (uint32_t)L.cout;  // 2 halves x 2 accumulator stages
+  tmem_cols = tmem_cols <= 32 ? 32 : tmem_cols <= 64 ? 64 : tmem_cols <= 128 ? 128 : tmem_cols <= 256 ? 256 : 512;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], H_MMA_WARPS);
+      mbar_init(&tfull_bar[s], H_MMA_WARPS);
+      mbar_init(&tempty_bar[s], H_EPI_WARPS);
+    }
+    for (int s = 0; s < H_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], H_MMA_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int c = threadIdx.x; c < L.cout; c += blockDim.x) s_bias[c] = bias[c];
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer ======================================================================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a0) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a1) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+      int bstage = 0, it = 0;
+      uint32_t bphase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int g0 = L.guard + t * 256 - L.halo;
+        mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&a_full[buf], a_buf);
+        for (int kk = 0; kk < kc; ++kk) {
+          unsigned char* dst = smA + (size_t)buf * a_buf_max + (size_t)kk * a_chunk;
+          tma_load_2d(dst, &map_a0, &a_full[buf], kk * TC_BK, g0);
+          tma_load_2d(dst + 256 * 128, &map_a1, &a_full[buf], kk * TC_BK, g0 + 256);
+        }
+        for (int tap = 0; tap < 9; ++tap)
+          for (int kk = 0; kk < kc; ++kk) {
+            mbar_wait(&b_empty[bstage], bphase ^ 1);
+            mbar_expect_tx(&b_full[bstage], b_bytes);
+            tma_load_2d(smB + (size_t)bstage * b_bytes, &map_b, &b_full[bstage], kk * TC_BK, tap * L.cout);
+            if (++bstage == H_BSTAGES) { bstage = 0; bphase ^= 1; }
+          }
+      }
+    }
+  } else if (warp <= H_MMA_WARPS) {
+    // ===== MMA issuers: warp 1 owns the upper 128 rows of the tile, warp 2 the lower 128 ==========
+    // The whole warp runs the loop (uniform control flow, descriptors precomputed); one elected lane issues.
+    const int h = warp - 1;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(L.cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO | version 1 | SWIZZLE_128B  (bits 32..63)
+    uint32_t b_lo[H_BSTAGES];
+#pragma unroll
+    for (int s2 = 0; s2 < H_BSTAGES; ++s2) b_lo[s2] = ((smem_u32(smB + (size_t)s2 * b_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+    const bool leader = elect_one();
+    int bstage = 0, it = 0;
+    uint32_t bphase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1, acc = it & 1;
+      mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
+      mbar_wait(&a_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      // start-address field (>>4) of output row 0 of this half, tap (0,0), channel chunk 0
+      const uint32_t a_lo0 = (((smem_u32(smA + (size_t)buf * a_buf_max) + (uint32_t)(h * 128 + L.halo) * 128u) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t d_tmem = tmem_base + (uint32_t)((acc * 2 + h) * L.cout);
+      for (int tap = 0; tap < 9; ++tap) {
+        const int toff8 = ((tap / 3 - 1) * L.Wr + (tap % 3 - 1)) * 8;  // rows -> 16-byte units
+        for (int kk = 0; kk < kc; ++kk) {
+          mbar_wait(&b_full[bstage], bphase);
+          tc_fence_after();
+          if (leader) {
+            const uint32_t alo = (uint32_t)((int)a_lo0 + toff8) + (uint32_t)kk * (a_chunk >> 4);
+            const uint32_t blo = b_lo[bstage];
+#pragma unroll
+            for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
+              const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(alo + (uint32_t)k4 * 2u);
+              const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(blo + (uint32_t)k4 * 2u);
+              tc_mma(d_tmem, ad, bd, idesc, (tap | kk | k4) != 0 ? 1u : 0u);
+            }
+            tc_commit(&b_empty[bstage]);
+          }
+          __syncwarp();
+          if (++bstage == H_BSTAGES) { bstage = 0; bphase ^= 1; }
+        }
+      }
+      if (leader) {
+        tc_commit(&tfull_bar[acc]);
+        tc_commit(&a_empty[buf]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue: 8 warps, two per TMEM lane quarter (column halves) ==========================
+    const int ew = warp - (1 + H_MMA_WARPS);  // 0..7
+    const int q = warp & 3;                   // TMEM lane quarter this warp may read
+    const int ch = ew >> 2;                   // column half
+    const int col0 = ch * cw;
+    unsigned char* stage = smS + (size_t)ew * 32 * srow;
+    const int lpr = (cw * 2) / 16;    // lanes per row in the coalesced phases (8 for 64 columns, 4 for 32)
+    const int rpi = 32 / lpr;         // rows per instruction
+    const int nld = 32 / rpi;         // coalesced instructions per 32-row pass (<= 8)
+    const int crow = lane / lpr, cchunk = lane - crow * lpr;
+    uint4 pre[8];                     // residual rows of the NEXT pass, in flight while the current one is processed
+    auto prefetch = [&](long long m_base) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        pre[i] = make_uint4(0, 0, 0, 0);
+        if (i < nld) {
+          const long long mr = m_base + i * rpi + crow;
+          if (mr < M) pre[i] = *reinterpret_cast<const uint4*>(res + ((size_t)L.guard + (size_t)mr) * L.cout + col0 + cchunk * 8);
+        }
+      }
+    };
+    int it = 0;
+    if (L.has_res && (int)blockIdx.x < num_tiles) prefetch((long long)blockIdx.x * 256 + q * 32);
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const long long m_base = (long long)t * 256 + h * 128 + q * 32;
+        if (L.has_res) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i < nld) *reinterpret_cast<uint4*>(stage + (size_t)(i * rpi + crow) * srow + cchunk * 16) = pre[i];
+          // next pass: other half of this tile, or the first half of this CTA's next tile
+          const long long nxt = h == 0 ? m_base + 128 : (long long)(t + gridDim.x) * 256 + q * 32;
+          if (h == 0 || t + (int)gridDim.x < num_tiles) prefetch(nxt);
+        }
+        __syncwarp();
+        const long long m = m_base + lane;
+        const int r = (int)(m % L.RP);
+        const int yy = r / L.Wr, xx = r - yy * L.Wr;
+        const bool valid = (m < M) && yy < L.Hc && xx < L.Hc;
+        unsigned char* myrow = stage + (size_t)lane * srow;
+        for (int c0 = 0; c0 < cw; c0 += 32) {
+          uint32_t v[32];
+          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * 2 + h) * L.cout + col0 + c0), v);
+          __align__(16) __nv_bfloat16 o[32];
+          if (valid) {
+            __align__(16) __nv_bfloat16 rr[32];
+            if (L.has_res) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) reinterpret_cast<uint4*>(rr)[k] = *reinterpret_cast<const uint4*>(myrow + c0 * 2 + k * 16);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float f = __uint_as_float(v[j]) + s_bias[col0 + c0 + j];
+              if (L.has_res) f += __bfloat162float(rr[j]);
+              if (L.relu) f = fmaxf(f, 0.f);
+              o[j] = __float2bfloat16(f);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __float2bfloat16(0.f);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(myrow + c0 * 2 + k * 16) = reinterpret_cast<const uint4*>(o)[k];
+        }
+        __syncwarp();
+        for (int r0 = 0; r0 < 32; r0 += rpi) {
+          const long long mr = m_base + r0 + crow;
+          if (mr < M)
+            *reinterpret_cast<uint4*>(out + ((size_t)L.guard + (size_t)mr) * L.cout + col0 + cchunk * 8) =
+                *reinterpret_cast<const uint4*>(stage + (size_t)(r0 + crow) * srow + cchunk * 16);
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -291,6 +538,25 @@ int aznet_tc_create(AzNet* n, AzRt& rt, std::string& err) {
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&tc->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  const char* md = getenv("AZ_TC_MODE");
+  tc->mode = md ? atoi(md) : 2;
+  if (n->C > 128) tc->mode = 0;  // the halo tile of a 256-channel layer does not fit next to the weight ring
+  if (tc->mode) {
+    tc->halo = n->g.Wr + 1;
+    tc->AR = (256 + 2 * tc->halo + 7) / 8 * 8;
+    const uint32_t tail = (uint32_t)(tc->AR - 256);
+    rc = make_map(&tc->hmap_in[0], n->act_in, 64, n->rows_total, 256, err);
+    if (!rc) rc = make_map(&tc->hmap_in[1], n->act_in, 64, n->rows_total, tail, err);
+    if (!rc) rc = make_map(&tc->hmap_x[0], n->act_x, n->C, n->rows_total, 256, err);
+    if (!rc) rc = make_map(&tc->hmap_x[1], n->act_x, n->C, n->rows_total, tail, err);
+    if (!rc) rc = make_map(&tc->hmap_mid[0], n->act_mid, n->C, n->rows_total, 256, err);
+    if (!rc) rc = make_map(&tc->hmap_mid[1], n->act_mid, n->C, n->rows_total, tail, err);
+    if (rc) return rc;
+    tc->halo_smem = (size_t)2 * 2 * tc->AR * 128 + (size_t)H_BSTAGES * n->C * TC_BK * 2 + (size_t)H_EPI_WARPS * 32 * (n->C + 16) + (size_t)n->C * 4 + 1024 + 256;
+    if (tc->halo_smem > 227 * 1024) { tc->mode = 0; return 0; }
+    e = cudaFuncSetAttribute(k_conv_tc_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc->halo_smem);
+    if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute(halo): ") + cudaGetErrorString(e); return AZ_ERR_CUDA; }
+  }
   return 0;
 }
 
@@ -339,6 +605,29 @@ int aznet_tc_forward(AzNet* n, AzRt& rt, const int8_t* obs_base, const int32_t* 
     rt.launches++;
   }
   const long long Mmax = (long long)max_rows * g.RP;
+  if (tc->mode) {
+    const int hgrid = (int)std::min<long long>((Mmax + 255) / 256, tc->num_sms);
+    HaloLayer H;
+    H.Wr = g.Wr; H.Hc = g.Hc; H.RP = g.RP; H.guard = g.guard; H.halo = tc->halo; H.AR = tc->AR; H.bo_mode = tc->mode == 1 ? 1 : 0;
+    __nv_bfloat16* X = (__nv_bfloat16*)n->act_x;
+    __nv_bfloat16* MID = (__nv_bfloat16*)n->act_mid;
+    H.cin = 64; H.cout = n->C; H.relu = 1; H.has_res = 0;
+    k_conv_tc_halo<<<hgrid, H_THREADS, tc->halo_smem, rt.stream>>>(tc->hmap_in[0], tc->hmap_in[1], tc->map_w[0], n->conv_b[0], nullptr, X, n_rows_dev, H);
+    rt.launches++;
+    H.cin = n->C;
+    for (int b = 0; b < n->blocks; ++b) {
+      H.has_res = 0;
+      k_conv_tc_halo<<<hgrid, H_THREADS, tc->halo_smem, rt.stream>>>(tc->hmap_x[0], tc->hmap_x[1], tc->map_w[1 + 2 * b], n->conv_b[1 + 2 * b], nullptr, MID, n_rows_dev, H);
+      H.has_res = 1;
+      k_conv_tc_halo<<<hgrid, H_THREADS, tc->halo_smem, rt.stream>>>(tc->hmap_mid[0], tc->hmap_mid[1], tc->map_w[2 + 2 * b], n->conv_b[2 + 2 * b], X, X, n_rows_dev, H);
+      rt.launches += 2;
+    }
+    launch_heads<__nv_bfloat16>(rt.stream, X, row_list, n_rows_dev, n->hp, g, n->C, n->A, n->fc, priors_base, values_base, pri_stride, max_rows);
+    rt.launches++;
+    cudaError_t he = cudaGetLastError();
+    if (he != cudaSuccess) { g_az_error = std::string("tensor-core tower (halo) launch: ") + cudaGetErrorString(he); return AZ_ERR_CUDA; }
+    return AZ_OK;
+  }
   const int grid = (int)std::min<long long>((Mmax + TC_BM - 1) / TC_BM, tc->num_sms);
   TcLayer L;
   L.Wr = g.Wr; L.Hc = g.Hc; L.RP = g.RP; L.guard = g.guard;
@@ -355,9 +644,7 @@ int aznet_tc_forward(AzNet* n, AzRt& rt, const int8_t* obs_base, const int32_t* 
     k_conv_tc<<<grid, TC_THREADS, tc->smem_bytes, rt.stream>>>(tc->map_mid, tc->map_w[2 + 2 * b], n->conv_b[2 + 2 * b], X, X, n_rows_dev, L);
     rt.launches += 2;
   }
-  const int HW = g.Hc * g.Hc;
-  const size_t head_smem = (size_t)(3 * HW + n->fc + n->A) * sizeof(float);
-  k_heads<__nv_bfloat16><<<max_rows, 128, head_smem, rt.stream>>>(X, row_list, n_rows_dev, n->hp, g, n->C, n->A, n->fc, priors_base, values_base, pri_stride);
+  launch_heads<__nv_bfloat16>(rt.stream, X, row_list, n_rows_dev, n->hp, g, n->C, n->A, n->fc, priors_base, values_base, pri_stride, max_rows);
   rt.launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_az_error = std::string("tensor-core tower launch: ") + cudaGetErrorString(e); return AZ_ERR_CUDA; }

@@ -11,7 +11,13 @@ def case(tag, prec):
         eng = Engine('gomoku' if gomoku else 'go', n, num_games=4, max_simulations=8, max_parallel=2, net=(nb, nf, fc), precision=prec)
         eng.set_weights(net.state_dict())
         pi, v = eng.net_forward(z[tag + '/x'])
-        print(tag, prec, 'max|dpi|', float(np.abs(pi - z[tag + '/pi']).max()), 'max|dv|', float(np.abs(v - z[tag + '/v'][:, 0]).max()), flush=True)
+        msg = ''
+        if prec == 'bf16':
+            from oracle import net as onet
+            lg, ve = onet.forward_bf16_emulated(net.state_dict(), torch.from_numpy(z[tag + '/x']).float(), bool(gomoku))
+            pe = torch.softmax(lg, -1).numpy()
+            msg = f' | vs bf16 emulation: max|dpi| {float(np.abs(pi - pe).max()):.2e} max|dv| {float(np.abs(v - ve.numpy()[:, 0]).max()):.2e}'
+        print(tag, prec, 'max|dpi|', float(np.abs(pi - z[tag + '/pi']).max()), 'max|dv|', float(np.abs(v - z[tag + '/v'][:, 0]).max()), msg, flush=True)
         eng.close()
     except Exception as ex:
         print(tag, prec, 'ERROR', repr(ex), flush=True)
