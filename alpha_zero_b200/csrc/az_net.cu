@@ -123,7 +123,7 @@ AzNet* aznet_create(const AzDims& d, const az_config& cfg, AzRt& rt, int max_lea
   if (n->C % 64 != 0 && n->precision == AZ_NET_BF16) { err = "bf16 tower needs num_filters to be a multiple of 64"; delete n; return nullptr; }
   if (n->C % 16 != 0 || n->C < 16) { err = "num_filters must be a multiple of 16"; delete n; return nullptr; }
   if (d.planes > g.cin_pad) { err = "observation has more than 32 planes"; delete n; return nullptr; }
-  n->rows_total = (size_t)max_leaves * g.RP + 2 * (size_t)g.guard + 512;
+  n->rows_total = (size_t)max_leaves * g.RP + 2 * (size_t)g.guard + 1024;
   const size_t esz = n->precision == AZ_NET_BF16 ? 2 : 4;
   n->act_in = rt_alloc(n->rows_total * g.cin_pad * esz);
   n->act_x = rt_alloc(n->rows_total * n->C * esz);

@@ -56,11 +56,26 @@ static __global__ void __launch_bounds__(256) k_heads(const T* __restrict__ feat
     const int y = pos / g.Hc, x = pos - y * g.Hc;
     const T* f = feat + ((size_t)g.guard + (size_t)(leaf0 + l) * g.RP + (size_t)y * g.Wr + x) * C;
     float p0 = 0.f, p1 = 0.f, v0 = 0.f;
-    for (int c = lane; c < C; c += 32) {
-      const float a = head_ld(f + c);
-      p0 = fmaf(a, hp.pol_w[c], p0);
-      p1 = fmaf(a, hp.pol_w[C + c], p1);
-      v0 = fmaf(a, hp.val_w[c], v0);
+    if (sizeof(T) == 2 && (C & 127) == 0) {
+      // bf16 rows: every lane takes 4 consecutive channels per 128-channel slab (one 8-byte load, float4 weights)
+      for (int c = lane * 4; c < C; c += 128) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(f) + (size_t)c * 2);
+        const float a0 = __uint_as_float(raw.x << 16), a1 = __uint_as_float(raw.x & 0xffff0000u);
+        const float a2 = __uint_as_float(raw.y << 16), a3 = __uint_as_float(raw.y & 0xffff0000u);
+        const float4 w0 = *reinterpret_cast<const float4*>(hp.pol_w + c);
+        const float4 w1 = *reinterpret_cast<const float4*>(hp.pol_w + C + c);
+        const float4 wv = *reinterpret_cast<const float4*>(hp.val_w + c);
+        p0 = fmaf(a0, w0.x, fmaf(a1, w0.y, fmaf(a2, w0.z, fmaf(a3, w0.w, p0))));
+        p1 = fmaf(a0, w1.x, fmaf(a1, w1.y, fmaf(a2, w1.z, fmaf(a3, w1.w, p1))));
+        v0 = fmaf(a0, wv.x, fmaf(a1, wv.y, fmaf(a2, wv.z, fmaf(a3, wv.w, v0))));
+      }
+    } else {
+      for (int c = lane; c < C; c += 32) {
+        const float a = head_ld(f + c);
+        p0 = fmaf(a, hp.pol_w[c], p0);
+        p1 = fmaf(a, hp.pol_w[C + c], p1);
+        v0 = fmaf(a, hp.val_w[c], v0);
+      }
     }
     for (int o = 16; o > 0; o >>= 1) {
       p0 += __shfl_xor_sync(0xffffffffu, p0, o);

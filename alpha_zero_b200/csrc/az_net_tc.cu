@@ -33,6 +33,7 @@ struct AzNetTc {
   int halo = 0, AR = 0;
   size_t halo_smem = 0;
   std::vector<CUtensorMap> map_w;
+  std::vector<CUtensorMap> map_w_half;  // pair kernel: box of cout/2 weight rows
   std::vector<__nv_bfloat16*> w_dev;
   int cin0 = 64;
   size_t smem_bytes = 0;
@@ -259,7 +260,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 // Epilogue: 8 warps (two per TMEM lane quarter, splitting the columns); residual rows are fetched and
 // results written back through a per-warp shared-memory staging tile so that every global access is a
 // full 128-byte line (the naive one-row-per-lane pattern issues 32 partial sectors per instruction).
-#define H_BSTAGES 3
+#define H_BSTAGES 4
 #define H_EPI_WARPS 8
 #define H_MMA_WARPS 2
 #define H_THREADS (32 * (1 + H_MMA_WARPS + H_EPI_WARPS))
@@ -271,12 +272,47 @@ struct HaloLayer {
   int bo_mode;    // experiment switch: 1 puts (start >> 7) & 7 into the descriptor's base-offset field (wrong on B200)
 };
 
+
+// ---- 2-CTA (cta_group::2) helpers ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (same shared-memory offset, CTA-rank bit cleared)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(x), "r"(y)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit that arrives on the barrier at the same offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
 
+template <bool PAIR>
 __global__ void __launch_bounds__(H_THREADS, 1)
 k_conv_tc_halo(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b,
                const float* __restrict__ bias, const __nv_bfloat16* res, __nv_bfloat16* out, const int32_t* __restrict__ n_rows, HaloLayer L) {
@@ -285,24 +321,30 @@ k_conv_tc_halo(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int kc = L.cin / TC_BK;
   const uint32_t a_chunk = (uint32_t)L.AR * 128u, a_buf = (uint32_t)kc * a_chunk;
   const uint32_t a_buf_max = 2u * a_chunk;  // buffers are carved for cin = 128
-  const uint32_t b_bytes = (uint32_t)L.cout * TC_BK * 2;
-  const int cw = L.cout / 2;                 // columns per epilogue warp
-  const uint32_t srow = (uint32_t)cw * 2 + 16;  // staging row pitch (bytes), +16 keeps 16-byte accesses conflict-free
+  const uint32_t b_bytes = (uint32_t)(PAIR ? L.cout / 2 : L.cout) * TC_BK * 2;  // a pair splits every weight chunk along N
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  constexpr int NB = PAIR ? 2 * H_BSTAGES : H_BSTAGES;                               // same bytes, twice the depth
+  const int cw = L.cout / 2;                 // columns per epilogue warp, processed 32 at a time
+  const uint32_t srow = 32 * 2 + 16;         // staging row pitch (bytes): 32 bf16 + 16 keeps 16-byte accesses conflict-free
   unsigned char* smA = smem;
   unsigned char* smB = smem + 2 * (size_t)a_buf_max;
-  unsigned char* smS = smB + (size_t)H_BSTAGES * b_bytes;
+  unsigned char* smS = smB + (size_t)NB * b_bytes;
   float* s_bias = (float*)(smS + (size_t)H_EPI_WARPS * 32 * srow);
   uint64_t* a_full = (uint64_t*)(s_bias + L.cout);
   uint64_t* a_empty = a_full + 2;
   uint64_t* b_full = a_empty + 2;
-  uint64_t* b_empty = b_full + H_BSTAGES;
-  uint64_t* tfull_bar = b_empty + H_BSTAGES;
+  uint64_t* b_empty = b_full + NB;
+  uint64_t* tfull_bar = b_empty + NB;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long M = (long long)(*n_rows) * L.RP;
-  const int num_tiles = (int)((M + 255) / 256);
+  const int num_tiles256 = (int)((M + 255) / 256);
+  // work unit: one 256-row tile per CTA; a pair takes two consecutive tiles (its CTAs differ in `crank`)
+  const int num_units = PAIR ? (num_tiles256 + 1) / 2 : num_tiles256;
+  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int ustep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   uint32_t tmem_cols = 4 * (uint32_t)L.cout;  // 2 halves x 2 accumulator stages
   tmem_cols = tmem_cols <= 32 ? 32 : tmem_cols <= 64 ? 64 : tmem_cols <= 128 ? 128 : tmem_cols <= 256 ? 256 : 512;
 
@@ -311,18 +353,24 @@ k_conv_tc_halo(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       mbar_init(&a_full[s], 1);
       mbar_init(&a_empty[s], H_MMA_WARPS);
       mbar_init(&tfull_bar[s], H_MMA_WARPS);
-      mbar_init(&tempty_bar[s], H_EPI_WARPS);
+      mbar_init(&tempty_bar[s], PAIR ? 2 * H_EPI_WARPS : H_EPI_WARPS);
     }
-    for (int s = 0; s < H_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], H_MMA_WARPS); }
+    for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], H_MMA_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int c = threadIdx.x; c < L.cout; c += blockDim.x) s_bias[c] = bias[c];
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers must exist before remote arrives / 2-SM TMA completions target them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -334,38 +382,59 @@ k_conv_tc_halo(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
       int bstage = 0, it = 0;
       uint32_t bphase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const int g0 = L.guard + t * 256 - L.halo;
-        mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1);
-        mbar_expect_tx(&a_full[buf], a_buf);
+      // the activation tile of iteration `j` (tile index tt) goes to buffer j&1; it is requested half a tile ahead
+      // u = work unit; this CTA's 256-row tile is u (single) or 2u + crank (pair).  In a pair only the leader arms the
+      // "full" barriers (with the bytes of BOTH CTAs); each CTA issues its own loads, credited to the leader's barrier.
+      auto load_a = [&](int j, int u) {
+        const int buf = j & 1;
+        const int tt = PAIR ? 2 * u + (int)crank : u;
+        const int g0 = L.guard + tt * 256 - L.halo;
+        mbar_wait(&a_empty[buf], ((j >> 1) & 1) ^ 1);
+        if (!PAIR) mbar_expect_tx(&a_full[buf], a_buf);
+        else if (crank == 0) mbar_expect_tx(&a_full[buf], 2 * a_buf);
         for (int kk = 0; kk < kc; ++kk) {
           unsigned char* dst = smA + (size_t)buf * a_buf_max + (size_t)kk * a_chunk;
-          tma_load_2d(dst, &map_a0, &a_full[buf], kk * TC_BK, g0);
-          tma_load_2d(dst + 256 * 128, &map_a1, &a_full[buf], kk * TC_BK, g0 + 256);
+          if (PAIR) {
+            tma_load_2d_pair(dst, &map_a0, &a_full[buf], kk * TC_BK, g0);
+            tma_load_2d_pair(dst + 256 * 128, &map_a1, &a_full[buf], kk * TC_BK, g0 + 256);
+          } else {
+            tma_load_2d(dst, &map_a0, &a_full[buf], kk * TC_BK, g0);
+            tma_load_2d(dst + 256 * 128, &map_a1, &a_full[buf], kk * TC_BK, g0 + 256);
+          }
         }
-        for (int tap = 0; tap < 9; ++tap)
+      };
+      if (unit0 < num_units) load_a(0, unit0);
+      for (int u = unit0; u < num_units; u += ustep, ++it) {
+        for (int tap = 0; tap < 9; ++tap) {
+          if (tap == 3 && u + ustep < num_units) load_a(it + 1, u + ustep);
           for (int kk = 0; kk < kc; ++kk) {
             mbar_wait(&b_empty[bstage], bphase ^ 1);
-            mbar_expect_tx(&b_full[bstage], b_bytes);
-            tma_load_2d(smB + (size_t)bstage * b_bytes, &map_b, &b_full[bstage], kk * TC_BK, tap * L.cout);
-            if (++bstage == H_BSTAGES) { bstage = 0; bphase ^= 1; }
+            if (PAIR) {
+              if (crank == 0) mbar_expect_tx(&b_full[bstage], 2 * b_bytes);
+              tma_load_2d_pair(smB + (size_t)bstage * b_bytes, &map_b, &b_full[bstage], kk * TC_BK, tap * L.cout + (int)crank * (L.cout / 2));
+            } else {
+              mbar_expect_tx(&b_full[bstage], b_bytes);
+              tma_load_2d(smB + (size_t)bstage * b_bytes, &map_b, &b_full[bstage], kk * TC_BK, tap * L.cout);
+            }
+            if (++bstage == NB) { bstage = 0; bphase ^= 1; }
           }
+        }
       }
     }
   } else if (warp <= H_MMA_WARPS) {
+   if (!PAIR || crank == 0) {
     // ===== MMA issuers: warp 1 owns the upper 128 rows of the tile, warp 2 the lower 128 ==========
     // The whole warp runs the loop (uniform control flow, descriptors precomputed); one elected lane issues.
     const int h = warp - 1;
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(L.cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(L.cout >> 3) << 17) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
     const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO | version 1 | SWIZZLE_128B  (bits 32..63)
-    uint32_t b_lo[H_BSTAGES];
+    uint32_t b_lo[NB];
 #pragma unroll
-    for (int s2 = 0; s2 < H_BSTAGES; ++s2) b_lo[s2] = ((smem_u32(smB + (size_t)s2 * b_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+    for (int s2 = 0; s2 < NB; ++s2) b_lo[s2] = ((smem_u32(smB + (size_t)s2 * b_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
     const bool leader = elect_one();
     int bstage = 0, it = 0;
     uint32_t bphase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int u = unit0; u < num_units; u += ustep, ++it) {
       const int buf = it & 1, acc = it & 1;
       mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
       mbar_wait(&a_full[buf], (it >> 1) & 1);
@@ -385,58 +454,97 @@ k_conv_tc_halo(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
               const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(alo + (uint32_t)k4 * 2u);
               const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(blo + (uint32_t)k4 * 2u);
-              tc_mma(d_tmem, ad, bd, idesc, (tap | kk | k4) != 0 ? 1u : 0u);
+              if (PAIR) tc_mma_pair(d_tmem, ad, bd, idesc, (tap | kk | k4) != 0 ? 1u : 0u);
+              else tc_mma(d_tmem, ad, bd, idesc, (tap | kk | k4) != 0 ? 1u : 0u);
             }
-            tc_commit(&b_empty[bstage]);
+            if (PAIR) tc_commit_pair(&b_empty[bstage]);
+            else tc_commit(&b_empty[bstage]);
           }
           __syncwarp();
-          if (++bstage == H_BSTAGES) { bstage = 0; bphase ^= 1; }
+          if (++bstage == NB) { bstage = 0; bphase ^= 1; }
         }
       }
       if (leader) {
-        tc_commit(&tfull_bar[acc]);
-        tc_commit(&a_empty[buf]);
+        if (PAIR) { tc_commit_pair(&tfull_bar[acc]); tc_commit_pair(&a_empty[buf]); }
+        else { tc_commit(&tfull_bar[acc]); tc_commit(&a_empty[buf]); }
       }
       __syncwarp();
     }
+   }
   } else {
     // ===== epilogue: 8 warps, two per TMEM lane quarter (column halves) ==========================
+    // A pass = 32 rows x 32 columns: residual (prefetched into registers one pass ahead) -> staging,
+    // tcgen05.ld, bias/residual/ReLU, bf16 -> staging, staging -> global.  Global accesses are 64-byte
+    // row segments (two full sectors), 8 rows per instruction.
     const int ew = warp - (1 + H_MMA_WARPS);  // 0..7
     const int q = warp & 3;                   // TMEM lane quarter this warp may read
     const int ch = ew >> 2;                   // column half
     const int col0 = ch * cw;
+    const int npass_c = cw / 32;              // column passes per half-tile (2 for 128 filters, 1 for 64)
     unsigned char* stage = smS + (size_t)ew * 32 * srow;
-    const int lpr = (cw * 2) / 16;    // lanes per row in the coalesced phases (8 for 64 columns, 4 for 32)
-    const int rpi = 32 / lpr;         // rows per instruction
-    const int nld = 32 / rpi;         // coalesced instructions per 32-row pass (<= 8)
-    const int crow = lane / lpr, cchunk = lane - crow * lpr;
-    uint4 pre[8];                     // residual rows of the NEXT pass, in flight while the current one is processed
-    auto prefetch = [&](long long m_base) {
+    const int crow = lane >> 2, cchunk = lane & 3;  // coalesced phases: 4 lanes x 16 B per row, 8 rows per instruction
+    uint4 pre[4];
+    auto prefetch = [&](long long m_base, int cc) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
+        const long long mr = m_base + i * 8 + crow;
         pre[i] = make_uint4(0, 0, 0, 0);
-        if (i < nld) {
-          const long long mr = m_base + i * rpi + crow;
-          if (mr < M) pre[i] = *reinterpret_cast<const uint4*>(res + ((size_t)L.guard + (size_t)mr) * L.cout + col0 + cchunk * 8);
-        }
+        if (mr < M) pre[i] = *reinterpret_cast<const uint4*>(res + ((size_t)L.guard + (size_t)mr) * L.cout + cc + cchunk * 8);
       }
     };
     int it = 0;
-    if (L.has_res && (int)blockIdx.x < num_tiles) prefetch((long long)blockIdx.x * 256 + q * 32);
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    const int tstep = PAIR ? 2 * ustep : ustep;  // distance between this CTA's consecutive 256-row tiles
+    const int t_first = PAIR ? 2 * unit0 + (int)crank : unit0;
+    if (L.has_res && L.bo_mode != 3 && unit0 < num_units) prefetch((long long)t_first * 256 + q * 32, col0);
+    for (int u = unit0; u < num_units; u += ustep, ++it) {
+      const int t = PAIR ? 2 * u + (int)crank : u;
       const int acc = it & 1;
       mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
+      for (int ps = 0; ps < 2 * npass_c; ++ps) {
+        const int h = ps / npass_c, pc = ps - h * npass_c;
+        const int cc = col0 + pc * 32;
         const long long m_base = (long long)t * 256 + h * 128 + q * 32;
+        if (L.bo_mode == 3) {
+          // experiment: no shared-memory staging, every lane reads / writes its own 64-byte row segment directly
+          const long long m = m_base + lane;
+          const int r = (int)(m % L.RP);
+          const int yy = r / L.Wr, xx = r - yy * L.Wr;
+          const bool valid = (m < M) && yy < L.Hc && xx < L.Hc;
+          const size_t grow = ((size_t)L.guard + (size_t)m) * L.cout + cc;
+          __align__(16) __nv_bfloat16 rr[32];
+          if (L.has_res && valid) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) reinterpret_cast<uint4*>(rr)[k] = reinterpret_cast<const uint4*>(res + grow)[k];
+          }
+          uint32_t v[32];
+          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * 2 + h) * L.cout + cc), v);
+          if (m < M) {
+            __align__(16) __nv_bfloat16 o[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float f = __uint_as_float(v[j]) + s_bias[cc + j];
+              if (L.has_res) f += __bfloat162float(rr[j]);
+              if (L.relu) f = fmaxf(f, 0.f);
+              o[j] = __float2bfloat16(valid ? f : 0.f);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) reinterpret_cast<uint4*>(out + grow)[k] = reinterpret_cast<const uint4*>(o)[k];
+          }
+          continue;
+        }
         if (L.has_res) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (i < nld) *reinterpret_cast<uint4*>(stage + (size_t)(i * rpi + crow) * srow + cchunk * 16) = pre[i];
-          // next pass: other half of this tile, or the first half of this CTA's next tile
-          const long long nxt = h == 0 ? m_base + 128 : (long long)(t + gridDim.x) * 256 + q * 32;
-          if (h == 0 || t + (int)gridDim.x < num_tiles) prefetch(nxt);
+          for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stage + (size_t)(i * 8 + crow) * srow + cchunk * 16) = pre[i];
+          // next pass of this tile, or the first pass of this CTA's next tile
+          const int nps = ps + 1;
+          if (nps < 2 * npass_c) {
+            const int nh = nps / npass_c, npc = nps - nh * npass_c;
+            prefetch((long long)t * 256 + nh * 128 + q * 32, col0 + npc * 32);
+          } else if (u + ustep < num_units) {
+            prefetch((long long)(t + tstep) * 256 + q * 32, col0);
+          }
         }
         __syncwarp();
         const long long m = m_base + lane;
@@ -444,19 +552,19 @@ k_conv_tc_halo(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const int yy = r / L.Wr, xx = r - yy * L.Wr;
         const bool valid = (m < M) && yy < L.Hc && xx < L.Hc;
         unsigned char* myrow = stage + (size_t)lane * srow;
-        for (int c0 = 0; c0 < cw; c0 += 32) {
+        {
           uint32_t v[32];
-          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * 2 + h) * L.cout + col0 + c0), v);
+          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * 2 + h) * L.cout + cc), v);
           __align__(16) __nv_bfloat16 o[32];
           if (valid) {
             __align__(16) __nv_bfloat16 rr[32];
             if (L.has_res) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) reinterpret_cast<uint4*>(rr)[k] = *reinterpret_cast<const uint4*>(myrow + c0 * 2 + k * 16);
+              for (int k = 0; k < 4; ++k) reinterpret_cast<uint4*>(rr)[k] = *reinterpret_cast<const uint4*>(myrow + k * 16);
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              float f = __uint_as_float(v[j]) + s_bias[col0 + c0 + j];
+              float f = __uint_as_float(v[j]) + s_bias[cc + j];
               if (L.has_res) f += __bfloat162float(rr[j]);
               if (L.relu) f = fmaxf(f, 0.f);
               o[j] = __float2bfloat16(f);
@@ -466,27 +574,33 @@ k_conv_tc_halo(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             for (int j = 0; j < 32; ++j) o[j] = __float2bfloat16(0.f);
           }
 #pragma unroll
-          for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(myrow + c0 * 2 + k * 16) = reinterpret_cast<const uint4*>(o)[k];
+          for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(myrow + k * 16) = reinterpret_cast<const uint4*>(o)[k];
         }
         __syncwarp();
-        for (int r0 = 0; r0 < 32; r0 += rpi) {
-          const long long mr = m_base + r0 + crow;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const long long mr = m_base + i * 8 + crow;
           if (mr < M)
-            *reinterpret_cast<uint4*>(out + ((size_t)L.guard + (size_t)mr) * L.cout + col0 + cchunk * 8) =
-                *reinterpret_cast<const uint4*>(stage + (size_t)(r0 + crow) * srow + cchunk * 16);
+            *reinterpret_cast<uint4*>(out + ((size_t)L.guard + (size_t)mr) * L.cout + cc + cchunk * 8) =
+                *reinterpret_cast<const uint4*>(stage + (size_t)(i * 8 + crow) * srow + cchunk * 16);
         }
         __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (PAIR && crank != 0) mbar_arrive_remote(&tempty_bar[acc], 0);  // the leader's MMA warps wait for both CTAs' drains
+        else mbar_arrive(&tempty_bar[acc]);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
@@ -539,7 +653,7 @@ int aznet_tc_create(AzNet* n, AzRt& rt, std::string& err) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&tc->num_sms, cudaDevAttrMultiProcessorCount, dev);
   const char* md = getenv("AZ_TC_MODE");
-  tc->mode = md ? atoi(md) : 2;
+  tc->mode = md ? atoi(md) : 4;  // 4 = halo tile + 2-CTA pairs (default), 2 = halo tile single CTA, 0 = one TMA box per tap
   if (n->C > 128) tc->mode = 0;  // the halo tile of a 256-channel layer does not fit next to the weight ring
   if (tc->mode) {
     tc->halo = n->g.Wr + 1;
@@ -552,9 +666,10 @@ int aznet_tc_create(AzNet* n, AzRt& rt, std::string& err) {
     if (!rc) rc = make_map(&tc->hmap_mid[0], n->act_mid, n->C, n->rows_total, 256, err);
     if (!rc) rc = make_map(&tc->hmap_mid[1], n->act_mid, n->C, n->rows_total, tail, err);
     if (rc) return rc;
-    tc->halo_smem = (size_t)2 * 2 * tc->AR * 128 + (size_t)H_BSTAGES * n->C * TC_BK * 2 + (size_t)H_EPI_WARPS * 32 * (n->C + 16) + (size_t)n->C * 4 + 1024 + 256;
+    tc->halo_smem = (size_t)2 * 2 * tc->AR * 128 + (size_t)H_BSTAGES * n->C * TC_BK * 2 + (size_t)H_EPI_WARPS * 32 * 80 + (size_t)n->C * 4 + 1024 + 256;
     if (tc->halo_smem > 227 * 1024) { tc->mode = 0; return 0; }
-    e = cudaFuncSetAttribute(k_conv_tc_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc->halo_smem);
+    e = cudaFuncSetAttribute(k_conv_tc_halo<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc->halo_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_tc_halo<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc->halo_smem);
     if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute(halo): ") + cudaGetErrorString(e); return AZ_ERR_CUDA; }
   }
   return 0;
@@ -573,6 +688,7 @@ int aznet_tc_set_weights(AzNet* n, AzRt& rt, std::string& err) {
   for (auto* p : tc->w_dev) rt_free(p);
   tc->w_dev.clear();
   tc->map_w.clear();
+  tc->map_w_half.clear();
   const int C = n->C;
   for (size_t li = 0; li < n->host_w.size(); ++li) {
     const int cin_src = li == 0 ? n->g.cin_pad : C;  // layer 0 was folded with the input rows' channel padding (64 here)
@@ -590,6 +706,10 @@ int aznet_tc_set_weights(AzNet* n, AzRt& rt, std::string& err) {
     int rc = make_map(&m, d, (uint64_t)cin, (uint64_t)9 * C, (uint32_t)C, err);
     if (rc) return rc;
     tc->map_w.push_back(m);
+    CUtensorMap mh;
+    rc = make_map(&mh, d, (uint64_t)cin, (uint64_t)9 * C, (uint32_t)(C / 2), err);
+    if (rc) return rc;
+    tc->map_w_half.push_back(mh);
   }
   return 0;
 }
@@ -606,21 +726,38 @@ int aznet_tc_forward(AzNet* n, AzRt& rt, const int8_t* obs_base, const int32_t* 
   }
   const long long Mmax = (long long)max_rows * g.RP;
   if (tc->mode) {
-    const int hgrid = (int)std::min<long long>((Mmax + 255) / 256, tc->num_sms);
+    const int hgrid = (int)std::max<long long>(2, std::min<long long>((Mmax + 255) / 256, tc->num_sms));
     HaloLayer H;
-    H.Wr = g.Wr; H.Hc = g.Hc; H.RP = g.RP; H.guard = g.guard; H.halo = tc->halo; H.AR = tc->AR; H.bo_mode = tc->mode == 1 ? 1 : 0;
+    H.Wr = g.Wr; H.Hc = g.Hc; H.RP = g.RP; H.guard = g.guard; H.halo = tc->halo; H.AR = tc->AR; H.bo_mode = tc->mode == 1 ? 1 : (tc->mode == 3 ? 3 : 0);
     __nv_bfloat16* X = (__nv_bfloat16*)n->act_x;
     __nv_bfloat16* MID = (__nv_bfloat16*)n->act_mid;
+    const bool pair = tc->mode == 4;
+    auto launch = [&](const CUtensorMap* ma, int wi, const float* bias, const __nv_bfloat16* resp, __nv_bfloat16* outp) {
+      if (!pair) {
+        k_conv_tc_halo<false><<<hgrid, H_THREADS, tc->halo_smem, rt.stream>>>(ma[0], ma[1], tc->map_w[wi], bias, resp, outp, n_rows_dev, H);
+      } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(hgrid & ~1));
+        cfg.blockDim = dim3(H_THREADS);
+        cfg.dynamicSmemBytes = tc->halo_smem;
+        cfg.stream = rt.stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, k_conv_tc_halo<true>, ma[0], ma[1], tc->map_w_half[wi], bias, resp, outp, n_rows_dev, H);
+      }
+      rt.launches++;
+    };
     H.cin = 64; H.cout = n->C; H.relu = 1; H.has_res = 0;
-    k_conv_tc_halo<<<hgrid, H_THREADS, tc->halo_smem, rt.stream>>>(tc->hmap_in[0], tc->hmap_in[1], tc->map_w[0], n->conv_b[0], nullptr, X, n_rows_dev, H);
-    rt.launches++;
+    launch(tc->hmap_in, 0, n->conv_b[0], nullptr, X);
     H.cin = n->C;
     for (int b = 0; b < n->blocks; ++b) {
       H.has_res = 0;
-      k_conv_tc_halo<<<hgrid, H_THREADS, tc->halo_smem, rt.stream>>>(tc->hmap_x[0], tc->hmap_x[1], tc->map_w[1 + 2 * b], n->conv_b[1 + 2 * b], nullptr, MID, n_rows_dev, H);
+      launch(tc->hmap_x, 1 + 2 * b, n->conv_b[1 + 2 * b], nullptr, MID);
       H.has_res = 1;
-      k_conv_tc_halo<<<hgrid, H_THREADS, tc->halo_smem, rt.stream>>>(tc->hmap_mid[0], tc->hmap_mid[1], tc->map_w[2 + 2 * b], n->conv_b[2 + 2 * b], X, X, n_rows_dev, H);
-      rt.launches += 2;
+      launch(tc->hmap_mid, 2 + 2 * b, n->conv_b[2 + 2 * b], X, X);
     }
     launch_heads<__nv_bfloat16>(rt.stream, X, row_list, n_rows_dev, n->hp, g, n->C, n->A, n->fc, priors_base, values_base, pri_stride, max_rows);
     rt.launches++;

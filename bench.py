@@ -314,7 +314,7 @@ def main():
             'e2e': {'value': e2e_sims / e2e_max, 'unit': 'simulations/s', 'h2d_bytes_per_step': int(eng.weight_bytes),
                     'd2h_bytes_per_step': int(d2h_bytes / max(1, a.steps)), 'samples_all_gathered': gathered},
             'gpu_launches': int(launches),
-            'roofline': {'bound': 'tensor', 'kernel': 'k_conv_tc' if a.precision == 'bf16' else 'k_conv_f32', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+            'roofline': {'bound': 'tensor', 'kernel': ('k_conv_tc_halo' if nf <= 128 and os.environ.get('AZ_TC_MODE', '2') != '0' else 'k_conv_tc') if a.precision == 'bf16' else 'k_conv_f32', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                          'frac': (achieved / peak) if achieved else None, 'traffic': None, 'peak_source': peak_src,
                          'note': f'algorithmic 2*MAC of one 3x3 conv layer ({conv_flops_per_eval / 1e6:.1f} MFLOP/leaf) x {tower_evals} leaves / mean launch time over the '
                                  f'{n_conv} tower launches of the last tick ({tower_ms:.3f} ms, CUDA events on the engine stream)'},

@@ -94,6 +94,28 @@ def test_net_bf16_matches_bf16_emulation(cuda, tag):
     eng.close()
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_net_19x19_256_filters(cuda, precision):
+    """The C5 geometry (19x19, 256 filters; N = 256 per MMA, per-tap TMA kernel): no reference golden travels for a net
+    this wide, so the checker is the oracle's torch forward (fp32: 1e-4) / its bf16 emulation (bf16: 1e-2) on the same weights."""
+    from alpha_zero_b200.engine import Engine
+    from alpha_zero_b200.network import AlphaZeroNet, randomize_batchnorm
+    from oracle import net as onet
+
+    torch.manual_seed(7)
+    net = randomize_batchnorm(AlphaZeroNet((17, 19, 19), 362, 2, 256, 256, False)).eval()
+    x = (torch.rand((5, 17, 19, 19)) < 0.3).to(torch.int8).numpy()
+    eng = Engine('go', 19, num_games=4, max_simulations=8, max_parallel=2, net=(2, 256, 256), precision=precision)
+    eng.set_weights(net.state_dict())
+    pi, v = eng.net_forward(x)
+    fwd = onet.forward if precision == 'fp32' else onet.forward_bf16_emulated
+    lg, vr = fwd(net.state_dict(), torch.from_numpy(x).float(), False)
+    tol = 1e-4 if precision == 'fp32' else 1e-2
+    np.testing.assert_allclose(pi, torch.softmax(lg, -1).numpy(), rtol=0, atol=tol)
+    np.testing.assert_allclose(v, vr.numpy()[:, 0], rtol=0, atol=2 * tol)
+    eng.close()
+
+
 @pytest.mark.parametrize('game', ['go9', 'gomoku13'])
 def test_search_with_cuda_net_vs_oracle(cuda, game):
     """Fixed-seed positions: pi from the CUDA search + CUDA fp32 net vs the oracle search + torch fp32 net: within 1e-3;
