@@ -18,30 +18,47 @@ struct Sim {
   int16_t* label;   // [ncp]
   int32_t* aux;     // [ncp]     liberties per group label / border flags per empty region
   uint8_t* legal;   // [Ap]
+  uint8_t* nbm;     // [ncp] neighbour mask per cell: bit0 down (+n), bit1 up (-n), bit2 right (+1), bit3 left (-1)
+  int32_t* path_k;  // [AZ_PATH] flat stats index (parent*Ap+move) of every node on the current descent
+  int16_t* path_n;  // [AZ_PATH] node ids
   int to_play, steps, h1, h2, ko, head;
   int labels_valid; // label[] / aux[] describe the stone groups of the current board
   int caps_b, caps_w;
 };
 
-AZ_DEV size_t sim_bytes(const AzDims& d) { return (size_t)d.ncp * 15 + d.Ap; }
+AZ_DEV size_t sim_bytes(const AzDims& d) { return (size_t)d.ncp * 16 + d.Ap + AZ_PATH * 6; }
 
 AZ_DEV void sim_carve(const AzDims& d, Sim& S, unsigned char* mem) {
+  S.path_k = (int32_t*)mem; mem += AZ_PATH * 4;
   S.aux = (int32_t*)mem;  mem += (size_t)d.ncp * 4;
   S.label = (int16_t*)mem; mem += (size_t)d.ncp * 2;
+  S.path_n = (int16_t*)mem; mem += AZ_PATH * 2;
   S.board = (int8_t*)mem;  mem += d.ncp;
   S.ring = (int8_t*)mem;   mem += (size_t)d.ncp * 8;
-  S.legal = (uint8_t*)mem;
+  S.legal = (uint8_t*)mem; mem += d.Ap;
+  S.nbm = (uint8_t*)mem;
+  // which neighbours exist, once per kernel: keeps integer divisions by the board size out of the rule loops
+  W_FOR(c, d.ncp) {
+    uint8_t m = 0;
+    if (c < d.nc) {
+      const int r = c / d.n, k = c - r * d.n;
+      m = (uint8_t)((r + 1 < d.n ? 1 : 0) | (r > 0 ? 2 : 0) | (k + 1 < d.n ? 4 : 0) | (k > 0 ? 8 : 0));
+    }
+    S.nbm[c] = m;
+  }
+  w_sync();
 }
 
 struct StepOut { int done; int reward_x2; int winner; int captured; float score; };
 
 #define AZ_NEIGHBOURS(d, c, q, BODY)                                         \
   {                                                                         \
-    int _r = (c) / (d).n, _k = (c) - _r * (d).n, q;                         \
-    if (_r + 1 < (d).n) { q = (c) + (d).n; BODY }                           \
-    if (_r > 0) { q = (c) - (d).n; BODY }                                   \
-    if (_k + 1 < (d).n) { q = (c) + 1; BODY }                               \
-    if (_k > 0) { q = (c)-1; BODY }                                         \
+    const int _m = S.nbm[(c)];                                              \
+    int q;                                                                  \
+    if (_m & 1) { q = (c) + (d).n; BODY }                                   \
+    if (_m & 2) { q = (c) - (d).n; BODY }                                   \
+    if (_m & 4) { q = (c) + 1; BODY }                                       \
+    if (_m & 8) { q = (c)-1; BODY }                                         \
   }
 
 // Load the position of slot g (global) into the scratch.

@@ -99,7 +99,7 @@ extern "C" int az_create(const az_config* cfg, az_engine** out) {
   d.G = cfg->num_games;
   d.Pmax = cfg->max_parallel;
   d.cap = cfg->max_simulations + 6 * cfg->max_parallel + 16;
-  if (d.cap > 32000) { delete e; return az_fail(AZ_ERR_CAPACITY, "az_create: node pool exceeds int16 child links"); }
+  if (d.cap > AZ_CIDX_MASK) { delete e; return az_fail(AZ_ERR_CAPACITY, "az_create: node pool exceeds the 14-bit child links"); }
   d.pass_move = cfg->game == AZ_GAME_GO ? d.nc : -1;
   d.table_len = d.cap + 64;
   d.max_len = (cfg->game == AZ_GAME_GO ? d.max_steps : d.nc) + 1;
@@ -146,6 +146,9 @@ extern "C" int az_create(const az_config* cfg, az_engine** out) {
   E.leaf_rows = dev_alloc<int32_t>(e, rows);
   E.leaf_total = dev_alloc<int32_t>(e, 4);
   E.leaf_count = dev_alloc<int32_t>(e, G);
+  E.leaf_pk = dev_alloc<int32_t>(e, rows * AZ_PATH);
+  E.leaf_pn = dev_alloc<int16_t>(e, rows * AZ_PATH);
+  E.leaf_depth = dev_alloc<int32_t>(e, rows);
   E.res_pi = dev_alloc<double>(e, G * d.Ap);
   E.res_q = dev_alloc<double>(e, G * 2);
   E.res_move = dev_alloc<int32_t>(e, G);

@@ -113,6 +113,9 @@ struct AzState {
   int32_t* leaf_rows;   // compacted list of occupied rows g*Pmax+j
   int32_t* leaf_total;  // [0] number of occupied rows, [1] active searches
   int32_t* leaf_count;  // [G] leaves per slot of the last collect pass
+  int32_t* leaf_pk;     // [G*Pmax][AZ_PATH] flat (parent*Ap+move) indices of the leaf's path, root side first
+  int16_t* leaf_pn;     // [G*Pmax][AZ_PATH] node ids along the path
+  int32_t* leaf_depth;  // [G*Pmax]
   // search results
   double* res_pi;       // [G][Ap]
   double* res_q;        // [G][2] root_Q, best_child_Q
@@ -137,3 +140,6 @@ enum { CT_SIMS = 0, CT_EVALS, CT_MOVES, CT_GAMES, CT_NODES, CT_DEPTH, CT_DESCENT
 enum { GR_SLOT = 0, GR_LEN, GR_WINNER, GR_BY_RESIGN, GR_SCORE_BITS, GR_PASSES, GR_RESIGN_DISABLED, GR_MARKED_FOR_RESIGN,
        GR_COULD_WON, GR_MARKED_PLAYER, GR_FIRST_LO, GR_FIRST_HI, GR_UID, GR_INTS = 16 };
 #define AZ_GAMES_RING 4096
+#define AZ_PATH 64          // recorded path length; deeper leaves fall back to the serial parent walk
+#define AZ_CIDX_EXPANDED 0x4000  // child link flag: the child is already expanded (saves a dependent load per level)
+#define AZ_CIDX_MASK 0x3FFF

@@ -61,23 +61,24 @@ AZ_DEV void tree_init_node(const AzState& E, TreeView& T, int idx, int parent, i
   }
 }
 
-// Lazy child creation at selection time (mcts_v2.py:182-183).
-AZ_DEV int tree_new_node(const AzState& E, TreeView& T, int g, int parent, int move, int to_play, LocalCounters& lc) {
-  int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
-  const int idx = ti[TI_NODES];
+// Lazy child creation at selection time (mcts_v2.py:182-183).  `n_nodes` is the caller's register copy of the pool size.
+AZ_DEV int tree_new_node(const AzState& E, TreeView& T, int parent, int move, int to_play, int& n_nodes, LocalCounters& lc) {
+  const int idx = n_nodes;
   if (idx >= E.d.cap) { lc.errors++; return -1; }
   tree_init_node(E, T, idx, parent, move, to_play);
-  W_LANE0 {
-    T.cidx[(size_t)parent * E.d.Ap + move] = (int16_t)idx;
-    ti[TI_NODES] = idx + 1;
-  }
+  W_LANE0 T.cidx[(size_t)parent * E.d.Ap + move] = (int16_t)idx;
   w_sync();
+  n_nodes = idx + 1;
   lc.nodes++;
   return idx;
 }
 
 // argmax_a ( -Q(a) + U(a) ) over legal a with numpy's float semantics; lowest index wins ties.
-AZ_DEV int tree_pick(const AzState& E, const TreeView& T, int g, int node, const uint8_t* legal) {
+// `n_node` is the visit count of `node` (its entry in the parent's row, already in a register from the level
+// above; unused for the root).  Besides the action the caller gets the child's link (index | expanded flag, or
+// -1) and the child's visit count, both taken from the rows this pick loaded anyway: a level of the descent
+// costs ONE round of independent global loads.
+AZ_DEV int tree_pick(const AzState& E, const TreeView& T, int g, int node, const uint8_t* legal, float n_node, int& child_link, float& n_child) {
   const int Ap = E.d.Ap;
   const int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
   double pbc;
@@ -89,7 +90,7 @@ AZ_DEV int tree_pick(const AzState& E, const TreeView& T, int g, int node, const
     pbc = ti[TI_ROOT_FRESH] ? E.pbc_fresh[n_i] : E.pbc_f32[n_i];
     use64 = ti[TI_ROOT_NOISED] != 0;
   } else {
-    n_i = (int)T.N[(size_t)T.parent[node] * Ap + T.pmove[node]];
+    n_i = (int)n_node;
     if (n_i >= E.d.table_len) n_i = E.d.table_len - 1;
     pbc = E.pbc_f32[n_i];
   }
@@ -98,20 +99,26 @@ AZ_DEV int tree_pick(const AzState& E, const TreeView& T, int g, int node, const
   const float* rN = T.N + (size_t)node * Ap;
   const float* rW = T.W + (size_t)node * Ap;
   const float* rP = T.P + (size_t)node * Ap;
+  const int16_t* rC = T.cidx + (size_t)node * Ap;
   const double* p64 = E.root_p64 + (size_t)g * Ap;
   double best = -1e300;
-  int bi = 1 << 30;
+  int bi = 1 << 30, bc = -1;
+  float bn = 0.f;
   W_FOR(a, E.d.A) {
     const float n_a = rN[a];
+    const int c_a = rC[a];
     const float ratio = f_div(s32, f_add(1.0f, n_a));
     const float q = f_div(rW[a], n_a > 0.f ? n_a : 1.0f);
     double sc;
     if (use64) sc = d_add((double)(-q), d_mul(d_mul(pbc, p64[a]), (double)ratio));
     else sc = (double)f_add(-q, f_mul(f_mul(pbc32, rP[a]), ratio));
     if (legal[a] != 1) sc = -9999.0;
-    if (sc > best) { best = sc; bi = a; }
+    if (sc > best) { best = sc; bi = a; bc = c_a; bn = n_a; }
   }
   w_argmax(best, bi);
+  // the winner is the local best of the lane that owns it (same tie-break locally and globally)
+  child_link = w_bcast_i(bc, bi);
+  n_child = w_bcast_f(bn, bi);
   return bi;
 }
 
@@ -162,10 +169,56 @@ AZ_DEV void tree_vloss(const AzState& E, TreeView& T, int g, int node, int sign)
   w_sync();
 }
 
+// ---- path-parallel statistics updates --------------------------------------------------------------
+// During a descent the flat statistics index k = parent*Ap + move and the node id of every step are
+// recorded (shared memory, then leaf_pk / leaf_pn in HBM for the apply pass).  Each node of a path is
+// touched exactly once by a virtual-loss / backup walk, so the lanes update them independently and get
+// bit-identical results to the reference's leaf-to-root loop.  Deeper than AZ_PATH: serial fallback.
+AZ_DEV void path_vloss(const AzState& E, TreeView& T, int g, const int32_t* pk, const int16_t* pn, int depth, int sign) {
+  const bool fresh = E.tree_i[(size_t)g * TREE_INTS + TI_ROOT_FRESH] != 0;
+  W_FOR(i, depth) {
+    const int node = pn[i];
+    bool touch = true;
+    if (sign > 0) T.vloss[node] += 1;
+    else if (T.vloss[node] > 0) T.vloss[node] -= 1;
+    else touch = false;
+    if (touch) T.W[pk[i]] = f_add(T.W[pk[i]], (float)sign);
+  }
+  W_LANE0 {
+    bool touch = true;
+    if (sign > 0) T.vloss[0] += 1;
+    else if (T.vloss[0] > 0) T.vloss[0] -= 1;
+    else touch = false;
+    if (touch) root_add_w(E, g, fresh, (float)sign);
+  }
+  w_sync();
+}
+
+// backup(leaf, value) (mcts_v2.py:213-232): element i of the path is (depth-1-i) plies above the leaf.
+AZ_DEV void path_backup(const AzState& E, TreeView& T, int g, const int32_t* pk, int depth, float value, LocalCounters& lc) {
+  W_FOR(i, depth) {
+    const float v = ((depth - 1 - i) & 1) ? -value : value;
+    T.N[pk[i]] = f_add(T.N[pk[i]], 1.0f);
+    T.W[pk[i]] = f_add(T.W[pk[i]], v);
+  }
+  W_LANE0 {
+    E.root_nw[(size_t)g * 2] += 1.0;
+    root_add_w(E, g, E.tree_i[(size_t)g * TREE_INTS + TI_ROOT_FRESH] != 0, (depth & 1) ? -value : value);
+  }
+  w_sync();
+  lc.sims++;
+}
+
 AZ_DEV void tree_expand(const AzState& E, TreeView& T, int node, const float* prior) {
   const int Ap = E.d.Ap;
   W_FOR(a, E.d.A) T.P[(size_t)node * Ap + a] = prior[a];
-  W_LANE0 T.expanded[node] = 1;
+  W_LANE0 {
+    T.expanded[node] = 1;
+    if (node != 0) {  // mirror the flag into the parent's link so that a descent does not have to load expanded[child]
+      const size_t k = (size_t)T.parent[node] * Ap + T.pmove[node];
+      T.cidx[k] = (int16_t)(T.cidx[k] | AZ_CIDX_EXPANDED);
+    }
+  }
   w_sync();
 }
 
@@ -272,44 +325,70 @@ AZ_DEV void game_collect(const AzState& E, int g, Sim& S, LocalCounters& lc) {
     if (st == ST_NEED_ROOT) {
       sim_load(E, g, S);
       sim_write_obs(d, S, E.leaf_obs + (size_t)g * d.Pmax * d.obs_bytes);
-      W_LANE0 E.leaf_node[(size_t)g * d.Pmax] = 0;
+      W_LANE0 { E.leaf_node[(size_t)g * d.Pmax] = 0; E.leaf_depth[(size_t)g * d.Pmax] = 0; }
       nleaves = 1;
     } else if (st == ST_SEARCHING) {
       TreeView T = tree_view(E, g, ti[TI_BUF]);
+      int n_nodes = ti[TI_NODES];
       int tries = 0;
       while (nleaves < E.s.P && tries < E.s.tries) {
         tries++;
         sim_load(E, g, S);
         int node = 0, depth = 0;
+        float n_cur = 0.f;
+        bool expanded_cur = true;  // the root of a running search is always expanded
         StepOut o;
         o.done = 0; o.reward_x2 = 0; o.winner = 0; o.captured = 0; o.score = 0.f;
         const uint8_t* legal = E.root_legal + (size_t)g * d.Ap;
         bool aborted = false;
-        while (T.expanded[node]) {
-          const int a = tree_pick(E, T, g, node, legal);
-          int child = T.cidx[(size_t)node * d.Ap + a];
-          if (child < 0) {
-            child = tree_new_node(E, T, g, node, a, -S.to_play, lc);
+        while (expanded_cur) {
+          int link;
+          float n_child;
+          const int a = tree_pick(E, T, g, node, legal, n_cur, link, n_child);
+          int child;
+          bool child_expanded = false;
+          if (link < 0) {
+            child = tree_new_node(E, T, node, a, -S.to_play, n_nodes, lc);
             if (child < 0) { aborted = true; break; }
+            n_child = 0.f;
+          } else {
+            child = link & AZ_CIDX_MASK;
+            child_expanded = (link & AZ_CIDX_EXPANDED) != 0;
+          }
+          if (depth < AZ_PATH) {
+            W_LANE0 { S.path_k[depth] = node * d.Ap + a; S.path_n[depth] = (int16_t)child; }
           }
           node = child;
+          n_cur = n_child;
           depth++;
           o = sim_play(d, S, a);
           legal = S.legal;
           if (o.done) break;
+          expanded_cur = child_expanded;
         }
         if (aborted) break;
+        w_sync();
         lc.descents++;
         lc.depth += depth;
         if (o.done) {  // terminal: never expanded, back up the game result (mcts_v2.py:604-608)
-          tree_backup(E, T, g, node, -(0.5f * (float)o.reward_x2), lc);
+          const float v = -(0.5f * (float)o.reward_x2);
+          if (depth <= AZ_PATH) path_backup(E, T, g, S.path_k, depth, v, lc);
+          else tree_backup(E, T, g, node, v, lc);
           continue;
         }
-        if (E.s.use_vloss) tree_vloss(E, T, g, node, +1);
-        W_LANE0 E.leaf_node[(size_t)g * d.Pmax + nleaves] = (int16_t)node;
-        sim_write_obs(d, S, E.leaf_obs + ((size_t)g * d.Pmax + nleaves) * d.obs_bytes);
+        if (E.s.use_vloss) {
+          if (depth <= AZ_PATH) path_vloss(E, T, g, S.path_k, S.path_n, depth, +1);
+          else tree_vloss(E, T, g, node, +1);
+        }
+        const size_t row = (size_t)g * d.Pmax + nleaves;
+        W_LANE0 { E.leaf_node[row] = (int16_t)node; E.leaf_depth[row] = depth; }
+        if (depth <= AZ_PATH) {
+          W_FOR(i, depth) { E.leaf_pk[row * AZ_PATH + i] = S.path_k[i]; E.leaf_pn[row * AZ_PATH + i] = S.path_n[i]; }
+        }
+        sim_write_obs(d, S, E.leaf_obs + row * d.obs_bytes);
         nleaves++;
       }
+      W_LANE0 ti[TI_NODES] = n_nodes;
     }
   }
   W_LANE0 ti[TI_NLEAVES] = nleaves;
@@ -345,11 +424,20 @@ AZ_DEV void game_apply(const AzState& E, int g, LocalCounters& lc) {
   if (st != ST_SEARCHING) return;
   const int n = ti[TI_NLEAVES];
   for (int j = 0; j < n; ++j) {
-    const int node = E.leaf_node[(size_t)g * d.Pmax + j];
-    if (E.s.use_vloss) tree_vloss(E, T, g, node, -1);
+    const size_t row = (size_t)g * d.Pmax + j;
+    const int node = E.leaf_node[row];
+    const int depth = E.leaf_depth[row];
+    const bool fast = depth <= AZ_PATH;
+    const int32_t* pk = E.leaf_pk + row * AZ_PATH;
+    const int16_t* pn = E.leaf_pn + row * AZ_PATH;
+    if (E.s.use_vloss) {
+      if (fast) path_vloss(E, T, g, pk, pn, depth, -1);
+      else tree_vloss(E, T, g, node, -1);
+    }
     if (T.expanded[node]) continue;  // same leaf picked twice in this batch (mcts_v2.py:619-622)
     tree_expand(E, T, node, pri + (size_t)j * d.Ap);
-    tree_backup(E, T, g, node, val[j], lc);
+    if (fast) path_backup(E, T, g, pk, depth, val[j], lc);
+    else tree_backup(E, T, g, node, val[j], lc);
   }
   if (E.root_nw[(size_t)g * 2] >= (double)E.s.sims_bound) {
     search_finish(E, g);
@@ -366,7 +454,8 @@ AZ_DEV int game_commit(const AzState& E, int g, int move, double* best_child_q) 
   int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
   const int buf = ti[TI_BUF];
   TreeView To = tree_view(E, g, buf);
-  const int child = (move >= 0 && move < d.A && ti[TI_NODES] > 0) ? To.cidx[move] : -1;
+  const int link0 = (move >= 0 && move < d.A && ti[TI_NODES] > 0) ? To.cidx[move] : -1;
+  const int child = link0 < 0 ? -1 : (link0 & AZ_CIDX_MASK);
   double bq = 0.0;
   int kept = 0;
   if (child >= 0) {
@@ -389,8 +478,8 @@ AZ_DEV int game_commit(const AzState& E, int g, int move, double* best_child_q) 
         const bool has = c >= 0;
         const uint32_t m = w_ballot(has);
         const int ni = base + az_popc(m & w_lanemask_lt());
-        if (has) { remap[ni] = (int16_t)c; Tn.parent[ni] = (int16_t)i; Tn.pmove[ni] = (int16_t)a; }
-        Tn.cidx[(size_t)i * Ap + a] = has ? (int16_t)ni : (int16_t)-1;
+        if (has) { remap[ni] = (int16_t)(c & AZ_CIDX_MASK); Tn.parent[ni] = (int16_t)i; Tn.pmove[ni] = (int16_t)a; }
+        Tn.cidx[(size_t)i * Ap + a] = has ? (int16_t)(ni | (c & AZ_CIDX_EXPANDED)) : (int16_t)-1;
         base += az_popc(m);
       }
       count = base;

@@ -27,6 +27,8 @@ AZ_DEV int w_min_i(int v) { return v; }
 AZ_DEV double w_sum_d(double v) { return v; }
 AZ_DEV float w_sum_f(float v) { return v; }
 AZ_DEV void w_argmax(double& v, int& i) { (void)v; (void)i; }
+AZ_DEV int w_bcast_i(int v, int) { return v; }
+AZ_DEV float w_bcast_f(float v, int) { return v; }
 AZ_DEV float f_mul(float a, float b) { return a * b; }  // built with -ffp-contract=off
 AZ_DEV float f_div(float a, float b) { return a / b; }
 AZ_DEV float f_add(float a, float b) { return a + b; }
@@ -75,6 +77,8 @@ AZ_DEV void w_argmax(double& v, int& i) {
     if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
   }
 }
+AZ_DEV int w_bcast_i(int v, int src) { return __shfl_sync(AZ_FULL, v, src & 31); }
+AZ_DEV float w_bcast_f(float v, int src) { return __shfl_sync(AZ_FULL, v, src & 31); }
 // Round-to-nearest, never contracted into FMA: the selection arithmetic must reproduce numpy's
 // element-wise float32 / float64 operations bit for bit.
 AZ_DEV float f_mul(float a, float b) { return __fmul_rn(a, b); }
