@@ -186,3 +186,92 @@ def mcts_traces(binding, game):
     assert c['errors'] == 0
     eng.close()
     return checked
+
+
+EXTRA = {  # name -> (game kind, board size, engine kwargs)
+    'random_go19': ('go', 19, {}),
+    'random_go13': ('go', 13, {'komi': 5.5, 'max_steps': 300}),
+    'random_go9': ('go', 9, {}),
+    'random_gomoku15': ('gomoku', 15, {}),
+    'pro_go9': ('go', 9, {}),
+}
+
+
+def replay_extra(binding, name, stride=1):
+    """Random-play / human-game corpora recorded from the reference: all games of a chunk advance in lock step."""
+    z = np.load(os.path.join(GOLDEN, f'{name}.npz'))
+    games = parse_corpus(z)
+    idx = list(range(0, len(games), stride))
+    kind, n, kw = EXTRA[name]
+    batch = min(64, len(idx))
+    eng = Engine(kind, n, num_games=batch, max_simulations=8, max_parallel=1, binding=binding, **kw)
+    bad = []
+    for b0 in range(0, len(idx), batch):
+        chunk = idx[b0:b0 + batch]
+        eng.env_reset(np.arange(len(chunk), dtype=np.int32))
+        trs = [Trajectory() for _ in chunk]
+        done = [False] * len(chunk)
+        for ply in range(max(len(games[g]) for g in chunk)):
+            live = [i for i, g in enumerate(chunk) if ply < len(games[g]) and not done[i]]
+            if not live:
+                break
+            r, d = eng.env_step(live, [int(games[chunk[i]][ply]) for i in live])
+            for k, i in enumerate(live):
+                trs[i].add(eng.env_legal(i), eng.env_board(i), r[k], d[k], eng.env_scalars(i)['to_play'])
+                done[i] = bool(d[k])
+        bad += [g for i, g in enumerate(chunk) if trs[i].hexdigest() != str(z['digest'][g])]
+    eng.close()
+    return bad, len(idx)
+
+
+def concurrent_searches(binding, game):
+    """Several slots searched in ONE batch (ragged: different positions, different carried subtrees, different leaf counts)
+    must each behave exactly as if searched alone: slot 0 replays a reference trace from its first ply, slots 1 and 3 start
+    from later positions of the same game and are compared with the oracle run from the same start.  Checks slot
+    independence, subtree reuse per slot and the leaf-row compaction order."""
+    from oracle.boards import GoBoard, GomokuBoard
+    from oracle.search import search
+
+    z = np.load(os.path.join(GOLDEN, f'mcts_{game}.npz'))
+    kind, n, A = ('go', 9, 82) if game == 'go9' else ('gomoku', 13, 169)
+    ev = make_fake_eval(A)
+    nm = 'par_det'
+    prefix, plies, sims, par, noise, det, warm_steps, reuse, seed = (int(v) for v in z[f'{nm}/cfg'])
+    assert not noise and det and reuse
+    eng = Engine(kind, n, num_games=4, max_simulations=sims + 8, max_parallel=par, binding=binding)
+    slots, starts = [0, 1, 3], [0, 2, 5]
+    moves = [int(m) for m in z[f'{nm}/move']]
+    oracles, roots = {}, {}
+    for s_, st in zip(slots, starts):
+        env = GoBoard(9) if game == 'go9' else GomokuBoard(13)
+        for a in [int(a) for a in z[f'{nm}/prefix']] + moves[:st]:
+            eng.env_step([s_], [a])
+            env.step(a)
+        oracles[s_], roots[s_] = env, None
+    for step in range(5):
+        warm = False  # deterministic play: warm-up only changes the exponent of pi, not the visit counts compared here
+        eng.search_begin(slots, [int(step > 0)] * 3, 19652.0, 1.25, sims, par, False, warm, True)
+        while True:
+            obs, counts, active = eng.search_select()
+            if active == 0:
+                break
+            if len(obs):
+                assert counts.sum() == len(obs)
+                pri, val = ev(obs, True)
+                eng.search_apply(np.stack(pri), np.array(val, dtype=np.float32))
+            else:
+                eng.search_apply(None, None)
+        for s_, st in zip(slots, starts):
+            res = eng.search_result(s_)
+            mv_o, pi, rq, cq, roots[s_], child_N = search(oracles[s_], ev, roots[s_], 19652.0, 1.25, sims, par, False, warm, True)
+            np.testing.assert_array_equal(res['child_N'], child_N, err_msg=f'slot {s_} step {step}')
+            assert res['argmax'] == mv_o and res['root_q'] == float(rq)
+            if st == 0:
+                np.testing.assert_array_equal(res['child_N'], z[f'{nm}/child_N'][step])
+                assert mv_o == moves[step]
+            bq, has = eng.search_commit(s_, mv_o)
+            assert bq == float(cq) and has == (roots[s_] is not None)
+            eng.env_step([s_], [mv_o])
+            oracles[s_].step(mv_o)
+    assert eng.counters()['errors'] == 0
+    eng.close()

@@ -521,6 +521,104 @@ def part_pipeline_gomoku13():
     np.savez_compressed(os.path.join(HERE, 'pipeline_gomoku13.npz'), **out)
 
 
+
+def _random_games(env, n_games, plies, seed, n):
+    """Seeded random legal play (passes allowed only when nothing else is legal) through the reference env."""
+    import numpy as np
+
+    rng = np.random.RandomState(seed)
+    all_moves, offsets, digests, results = [], [0], [], []
+    for _ in range(n_games):
+        env.reset()
+        tr = Trajectory()
+        for _ply in range(plies):
+            if env.is_game_over():
+                break
+            legal = np.flatnonzero(env.legal_actions)
+            if env.has_pass_move and len(legal) > 1:
+                legal = legal[legal != env.pass_move]
+            a = int(rng.choice(legal))
+            _, r, d, _ = env.step(a)
+            tr.add(env, r, d)
+            all_moves.append(a)
+        offsets.append(len(all_moves))
+        digests.append(tr.h.hexdigest())
+        results.append(env.get_result_string() if env.is_game_over() else '')
+    return dict(moves=np.array(all_moves, dtype=np.int16), offsets=np.array(offsets, dtype=np.int32), digest=np.array(digests),
+                result_env=np.array(results), versions=versions())
+
+
+def part_random_go19():
+    """Big-board coverage: 12 random 19x19 games of up to 420 plies (captures, ko, suicide masks on 361 cells)."""
+    import numpy as np
+    from alpha_zero.envs.go import GoEnv
+
+    out = _random_games(GoEnv(komi=7.5, num_stack=8), 12, 420, 19, 19)
+    np.savez_compressed(os.path.join(HERE, 'random_go19.npz'), **out)
+    print('random_go19: ok')
+
+
+def part_random_go13():
+    import numpy as np
+    from alpha_zero.envs.go import GoEnv
+
+    out = _random_games(GoEnv(komi=5.5, num_stack=8, max_steps=300), 24, 300, 13, 13)
+    np.savez_compressed(os.path.join(HERE, 'random_go13.npz'), **out)
+    print('random_go13: ok')
+
+
+def part_random_go9_full():
+    """Random 9x9 games played to the end (max_steps / double pass): scoring of crowded final positions."""
+    import numpy as np
+    from alpha_zero.envs.go import GoEnv
+
+    out = _random_games(GoEnv(komi=7.5, num_stack=8), 60, 400, 9, 9)
+    np.savez_compressed(os.path.join(HERE, 'random_go9.npz'), **out)
+    print('random_go9: ok', sum(1 for r in out['result_env'] if r))
+
+
+def part_random_gomoku15():
+    import numpy as np
+    from alpha_zero.envs.gomoku import GomokuEnv
+
+    out = _random_games(GomokuEnv(board_size=15, num_stack=8), 40, 225, 15, 15)
+    np.savez_compressed(os.path.join(HERE, 'random_gomoku15.npz'), **out)
+    print('random_gomoku15: ok')
+
+
+def part_pro_go9():
+    """Human games (games/pro_games/go/9x9): tougher fights than self-play.  First 1500 files, digests only."""
+    import numpy as np
+    from alpha_zero.envs.go import GoEnv
+
+    d = os.path.join(REF, 'games/pro_games/go/9x9')
+    files = sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith('.sgf'))[:1500]
+    env = GoEnv(komi=7.5, num_stack=8)
+    all_moves, offsets, digests, played = [], [0], [], []
+    for path in files:
+        try:
+            moves, _ = parse_sgf(open(path, errors='ignore').read(), 9)
+        except Exception:
+            moves = []
+        env.reset()
+        tr = Trajectory()
+        ok = []
+        for a in moves:
+            if env.is_game_over() or a > 81 or env.legal_actions[a] != 1:
+                break
+            _, r, dn, _ = env.step(a)
+            tr.add(env, r, dn)
+            ok.append(a)
+        all_moves.extend(ok)
+        offsets.append(len(all_moves))
+        digests.append(tr.h.hexdigest())
+        played.append(len(ok))
+    out = dict(moves=np.array(all_moves, dtype=np.int16), offsets=np.array(offsets, dtype=np.int32), digest=np.array(digests),
+               played=np.array(played, dtype=np.int32), versions=versions())
+    np.savez_compressed(os.path.join(HERE, 'pro_go9.npz'), **out)
+    print('pro_go9:', len(files), 'games,', len(all_moves), 'moves')
+
+
 PARTS = {
     'go9_selfplay': (part_go9_selfplay, 9),
     'gomoku13_selfplay': (part_gomoku13_selfplay, 9),
@@ -531,6 +629,11 @@ PARTS = {
     'net': (part_net, 9),
     'pipeline_go9': (part_pipeline_go9, 9),
     'pipeline_gomoku13': (part_pipeline_gomoku13, 9),
+    'random_go19': (part_random_go19, 19),
+    'random_go13': (part_random_go13, 13),
+    'random_go9': (part_random_go9_full, 9),
+    'random_gomoku15': (part_random_gomoku15, 9),
+    'pro_go9': (part_pro_go9, 9),
 }
 
 

@@ -43,3 +43,14 @@ def test_gomoku_unit(emu):
 @pytest.mark.parametrize('game', ['go9', 'gomoku13'])
 def test_mcts_traces(emu, game):
     assert enginecheck.mcts_traces(emu, game) > 50
+
+
+@pytest.mark.parametrize('name', sorted(enginecheck.EXTRA))
+def test_extra_corpora(emu, name):
+    bad, n = enginecheck.replay_extra(emu, name, stride=1 if name != 'pro_go9' else int(os.environ.get('AZ_CORPUS_STRIDE', '10')))
+    assert not bad, f'{name}: {len(bad)}/{n} games differ, first {bad[:5]}'
+
+
+@pytest.mark.parametrize('game', ['go9', 'gomoku13'])
+def test_concurrent_searches(emu, game):
+    enginecheck.concurrent_searches(emu, game)

@@ -48,6 +48,18 @@ def test_mcts_traces(cuda, game):
     assert enginecheck.mcts_traces(cuda, game) > 50
 
 
+@pytest.mark.parametrize('name', sorted(enginecheck.EXTRA))
+def test_extra_corpora(cuda, name):
+    """19x19 / 13x13 Go, 15x15 Gomoku random play and 1500 human 9x9 games recorded from the reference envs."""
+    bad, n = enginecheck.replay_extra(cuda, name, stride=1 if name != 'pro_go9' else int(os.environ.get('AZ_CORPUS_STRIDE', '2')))
+    assert not bad, f'{name}: {len(bad)}/{n} games differ, first {bad[:5]}'
+
+
+@pytest.mark.parametrize('game', ['go9', 'gomoku13'])
+def test_concurrent_searches(cuda, game):
+    enginecheck.concurrent_searches(cuda, game)
+
+
 def _net_case(tag):
     from alpha_zero_b200.network import AlphaZeroNet, randomize_batchnorm
 

@@ -108,3 +108,25 @@ def test_gomoku_unit_cases(golden_dir):
         assert (0 if env.winner is None else env.winner) == int(z[name + '/winner'][0])
         assert env.get_result_string() == str(z[name + '/result'][0])
         np.testing.assert_array_equal(env.observation(), z[name + '/obs'])
+
+
+EXTRA = [  # (file, constructor) -- random play and human games recorded from the reference (tests/golden/make_golden.py)
+    ('random_go19', lambda: GoBoard(19, 7.5, 8)),
+    ('random_go13', lambda: GoBoard(13, 5.5, 8, 300)),
+    ('random_go9', lambda: GoBoard(9, 7.5, 8)),
+    ('random_gomoku15', lambda: GomokuBoard(15, 5, 8)),
+    ('pro_go9', lambda: GoBoard(9, 7.5, 8)),
+]
+
+
+@pytest.mark.parametrize('name', [e[0] for e in EXTRA])
+def test_extra_corpora_digests(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, f'{name}.npz'))
+    games = parse_corpus(z)
+    env = dict(EXTRA)[name]()
+    stride = 1 if name != 'pro_go9' else int(os.environ.get('AZ_CORPUS_STRIDE', '6'))
+    for gi in range(0, len(games), stride):
+        tr, _ = _replay(env, games[gi])
+        assert tr.hexdigest() == str(z['digest'][gi]), (name, gi)
+        if 'result_env' in z.files:
+            assert (env.get_result_string() if env.is_game_over() else '') == str(z['result_env'][gi])
