@@ -239,6 +239,15 @@ int aznet_set_weights(AzNet* n, AzRt& rt, const float* const* T, const int64_t* 
   hp.pol_w = upload(rt, n->allocs, pw);
   hp.pol_b = upload(rt, n->allocs, pb);
   hp.pol_fc_w = upload(rt, n->allocs, pfw);
+  {
+    std::vector<float> t((size_t)2 * HW * A), u((size_t)HW * fc);
+    for (int a2 = 0; a2 < A; ++a2)
+      for (int k = 0; k < 2 * HW; ++k) t[(size_t)k * A + a2] = pfw[(size_t)a2 * 2 * HW + k];
+    for (int j = 0; j < fc; ++j)
+      for (int k = 0; k < HW; ++k) u[(size_t)k * fc + j] = v1w[(size_t)j * HW + k];
+    hp.pol_fc_wT = upload(rt, n->allocs, t);
+    hp.val_fc1_wT = upload(rt, n->allocs, u);
+  }
   hp.pol_fc_b = upload(rt, n->allocs, pfb);
   hp.val_w = upload(rt, n->allocs, vw);
   hp.val_b = upload(rt, n->allocs, vb);

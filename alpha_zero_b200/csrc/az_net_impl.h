@@ -21,6 +21,7 @@ struct NetGeom {
 
 struct HeadParams {
   const float *pol_w, *pol_b, *pol_fc_w, *pol_fc_b;
+  const float *pol_fc_wT, *val_fc1_wT;  // k-major copies of the FC weights: [2*HW][A], [HW][fc]
   const float *val_w, *val_b, *val_fc1_w, *val_fc1_b, *val_fc2_w, *val_fc2_b;
 };
 

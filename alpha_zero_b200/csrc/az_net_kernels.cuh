@@ -49,78 +49,70 @@ static __global__ void __launch_bounds__(256) k_heads(const T* __restrict__ feat
   extern __shared__ float sh[];
   const int HW = g.Hc * g.Hc;
   const int per = 3 * HW + fc + A;       // floats per leaf: pol[2*HW] | val[HW] | fc1[fc] | logits[A]
+  float* s_w = sh + (size_t)LPB * per;   // [3][C] folded 1x1 conv weights (policy 0, policy 1, value)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // ---- phase 1
-  for (int idx = warp; idx < nl * HW; idx += 8) {
+  for (int i = tid; i < 3 * C; i += 256) s_w[i] = i < 2 * C ? hp.pol_w[i] : hp.val_w[i - 2 * C];
+  __syncthreads();
+  // ---- phase 1: one thread per board position, channels streamed 16 bytes at a time, no shuffles
+  for (int idx = tid; idx < nl * HW; idx += 256) {
     const int l = idx / HW, pos = idx - l * HW;
     const int y = pos / g.Hc, x = pos - y * g.Hc;
     const T* f = feat + ((size_t)g.guard + (size_t)(leaf0 + l) * g.RP + (size_t)y * g.Wr + x) * C;
     float p0 = 0.f, p1 = 0.f, v0 = 0.f;
-    if (sizeof(T) == 2 && (C & 127) == 0) {
-      // bf16 rows: every lane takes 4 consecutive channels per 128-channel slab (one 8-byte load, float4 weights)
-      for (int c = lane * 4; c < C; c += 128) {
-        const uint2 raw = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(f) + (size_t)c * 2);
-        const float a0 = __uint_as_float(raw.x << 16), a1 = __uint_as_float(raw.x & 0xffff0000u);
-        const float a2 = __uint_as_float(raw.y << 16), a3 = __uint_as_float(raw.y & 0xffff0000u);
-        const float4 w0 = *reinterpret_cast<const float4*>(hp.pol_w + c);
-        const float4 w1 = *reinterpret_cast<const float4*>(hp.pol_w + C + c);
-        const float4 wv = *reinterpret_cast<const float4*>(hp.val_w + c);
-        p0 = fmaf(a0, w0.x, fmaf(a1, w0.y, fmaf(a2, w0.z, fmaf(a3, w0.w, p0))));
-        p1 = fmaf(a0, w1.x, fmaf(a1, w1.y, fmaf(a2, w1.z, fmaf(a3, w1.w, p1))));
-        v0 = fmaf(a0, wv.x, fmaf(a1, wv.y, fmaf(a2, wv.z, fmaf(a3, wv.w, v0))));
+    if (sizeof(T) == 2) {
+      const uint4* f4 = reinterpret_cast<const uint4*>(f);
+      for (int c8 = 0; c8 < C / 8; ++c8) {
+        const uint4 raw = f4[c8];
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float a0 = __uint_as_float(w[k] << 16), a1 = __uint_as_float(w[k] & 0xffff0000u);
+          const int c = c8 * 8 + k * 2;
+          p0 = fmaf(a0, s_w[c], fmaf(a1, s_w[c + 1], p0));
+          p1 = fmaf(a0, s_w[C + c], fmaf(a1, s_w[C + c + 1], p1));
+          v0 = fmaf(a0, s_w[2 * C + c], fmaf(a1, s_w[2 * C + c + 1], v0));
+        }
       }
     } else {
-      for (int c = lane; c < C; c += 32) {
+      for (int c = 0; c < C; ++c) {
         const float a = head_ld(f + c);
-        p0 = fmaf(a, hp.pol_w[c], p0);
-        p1 = fmaf(a, hp.pol_w[C + c], p1);
-        v0 = fmaf(a, hp.val_w[c], v0);
+        p0 = fmaf(a, s_w[c], p0);
+        p1 = fmaf(a, s_w[C + c], p1);
+        v0 = fmaf(a, s_w[2 * C + c], v0);
       }
     }
-    for (int o = 16; o > 0; o >>= 1) {
-      p0 += __shfl_xor_sync(0xffffffffu, p0, o);
-      p1 += __shfl_xor_sync(0xffffffffu, p1, o);
-      v0 += __shfl_xor_sync(0xffffffffu, v0, o);
-    }
-    if (lane == 0) {
-      float* s = sh + (size_t)l * per;
-      s[pos] = fmaxf(p0 + hp.pol_b[0], 0.f);
-      s[HW + pos] = fmaxf(p1 + hp.pol_b[1], 0.f);
-      s[2 * HW + pos] = fmaxf(v0 + hp.val_b[0], 0.f);
-    }
+    float* s = sh + (size_t)l * per;
+    s[pos] = fmaxf(p0 + hp.pol_b[0], 0.f);
+    s[HW + pos] = fmaxf(p1 + hp.pol_b[1], 0.f);
+    s[2 * HW + pos] = fmaxf(v0 + hp.val_b[0], 0.f);
   }
   __syncthreads();
-  // ---- phase 2
-  for (int a = warp; a < A + fc; a += 8) {
+  // ---- phase 2: one thread per FC output row (policy logits, value hidden units), LPB accumulators,
+  //      weights read k-major (transposed at az_set_weights) so that consecutive threads read consecutive floats
+  for (int a = tid; a < A + fc; a += 256) {
     float acc[LPB];
 #pragma unroll
     for (int l = 0; l < LPB; ++l) acc[l] = 0.f;
     const bool is_pol = a < A;
-    const float* wr = is_pol ? hp.pol_fc_w + (size_t)a * 2 * HW : hp.val_fc1_w + (size_t)(a - A) * HW;
-    const int klen = is_pol ? 2 * HW : HW;
-    const int soff = is_pol ? 0 : 2 * HW;
-    for (int k = lane; k < klen; k += 32) {
-      const float w = wr[k];
+    const float* wt = is_pol ? hp.pol_fc_wT + a : hp.val_fc1_wT + (a - A);
+    const int klen = is_pol ? 2 * HW : HW, ldw = is_pol ? A : fc, soff = is_pol ? 0 : 2 * HW;
+    for (int k = 0; k < klen; ++k) {
+      const float w = wt[(size_t)k * ldw];
 #pragma unroll
       for (int l = 0; l < LPB; ++l) acc[l] = fmaf(sh[(size_t)l * per + soff + k], w, acc[l]);
     }
+    const float bv = is_pol ? hp.pol_fc_b[a] : hp.val_fc1_b[a - A];
 #pragma unroll
-    for (int l = 0; l < LPB; ++l)
-      for (int o = 16; o > 0; o >>= 1) acc[l] += __shfl_xor_sync(0xffffffffu, acc[l], o);
-    if (lane == 0) {
-      const float bv = is_pol ? hp.pol_fc_b[a] : hp.val_fc1_b[a - A];
-#pragma unroll
-      for (int l = 0; l < LPB; ++l) {
-        if (l < nl) {
-          float* s = sh + (size_t)l * per;
-          if (is_pol) s[3 * HW + fc + a] = acc[l] + bv;
-          else s[3 * HW + (a - A)] = fmaxf(acc[l] + bv, 0.f);
-        }
+    for (int l = 0; l < LPB; ++l) {
+      if (l < nl) {
+        float* s = sh + (size_t)l * per;
+        if (is_pol) s[3 * HW + fc + a] = acc[l] + bv;
+        else s[3 * HW + (a - A)] = fmaxf(acc[l] + bv, 0.f);
       }
     }
   }
   __syncthreads();
-  // ---- phase 3
+  // ---- phase 3: softmax / value FC2 + tanh, one warp per leaf
   for (int l = warp; l < nl; l += 8) {
     float* s = sh + (size_t)l * per;
     float* lg = s + 3 * HW + fc;
@@ -149,10 +141,11 @@ static inline void launch_heads(cudaStream_t stream, const T* feat, const int32_
                                 const NetGeom& g, int C, int A, int fc, float* priors, float* values, int pri_stride, int max_rows) {
   const int HW = g.Hc * g.Hc;
   const size_t per = (size_t)(3 * HW + fc + A) * sizeof(float);
-  if (per * 8 <= 48 * 1024)
-    k_heads<T, 8><<<(max_rows + 7) / 8, 256, per * 8, stream>>>(feat, row_list, n_rows, hp, g, C, A, fc, priors, values, pri_stride);
-  else if (per * 4 <= 48 * 1024)
-    k_heads<T, 4><<<(max_rows + 3) / 4, 256, per * 4, stream>>>(feat, row_list, n_rows, hp, g, C, A, fc, priors, values, pri_stride);
+  const size_t wsm = (size_t)3 * C * sizeof(float);
+  if (per * 8 + wsm <= 48 * 1024)
+    k_heads<T, 8><<<(max_rows + 7) / 8, 256, per * 8 + wsm, stream>>>(feat, row_list, n_rows, hp, g, C, A, fc, priors, values, pri_stride);
+  else if (per * 4 + wsm <= 48 * 1024)
+    k_heads<T, 4><<<(max_rows + 3) / 4, 256, per * 4 + wsm, stream>>>(feat, row_list, n_rows, hp, g, C, A, fc, priors, values, pri_stride);
   else
-    k_heads<T, 1><<<max_rows, 256, per, stream>>>(feat, row_list, n_rows, hp, g, C, A, fc, priors, values, pri_stride);
+    k_heads<T, 1><<<max_rows, 256, per + wsm, stream>>>(feat, row_list, n_rows, hp, g, C, A, fc, priors, values, pri_stride);
 }

@@ -90,3 +90,53 @@ def test_actor_loop_emits_reference_shaped_items(tmp_path):
                               'marked_resign_player', 'resign_threshold', 'time_per_game', 'training_steps'}
         assert abs(float(seq[0].pi_prob.sum()) - 1.0) < 1e-5 and seq[0].value in (-1.0, 0.0, 1.0)
     assert os.path.exists(tmp_path / 'actor0.csv') and any(f.endswith('.sgf') for f in os.listdir(tmp_path))
+
+
+def test_actor_loop_as_spawned_process_with_ckpt_hot_swap(tmp_path):
+    """The deployment shape of the reference (training_go.py:276-345, 393): `spawn` start method, the env and the network
+    pickled into the child, manager Values for the checkpoint path / resign threshold, mp.Events, a bounded mp.Queue.
+    After the learner 'publishes' a checkpoint the emitted games carry its training_steps."""
+    from alpha_zero_b200.envs.gomoku import GomokuEnv
+    from alpha_zero_b200.network import AlphaZeroNet, randomize_batchnorm
+    from alpha_zero_b200.pipeline import run_selfplay_actor_loop
+
+    os.environ['AZ_ACTOR_GAMES'] = '64'
+    os.environ['AZ_NET_PRECISION'] = 'bf16'
+    ctx = mp.get_context('spawn')
+    torch.manual_seed(123)
+    net = randomize_batchnorm(AlphaZeroNet((17, 9, 9), 81, 2, 64, 64, True)).eval()
+    env = GomokuEnv(board_size=9, num_stack=8)
+    ckpt = tmp_path / 'training_steps_7.ckpt'
+    torch.save({'network': net.state_dict(), 'training_steps': 7}, ckpt)
+    stop, pause = ctx.Event(), ctx.Event()
+    q = ctx.Queue(maxsize=4)
+    with ctx.Manager() as manager:
+        var_ckpt = manager.Value('s', b'')
+        var_thr = manager.Value('d', -1.0)
+        p = ctx.Process(target=run_selfplay_actor_loop, args=(1, 3, net, torch.device('cuda:0'), q, env, 16, 4, 19652.0, 1.25, 4, 6, 0.5, str(tmp_path), 1000,
+                                                              str(tmp_path), None, 'INFO', var_ckpt, var_thr, pause, stop))
+        p.start()
+        try:
+            first = [q.get(timeout=180) for _ in range(10)]
+            assert all(st['training_steps'] == 0 for _, st in first)
+            var_ckpt.value = str(ckpt).encode('utf-8')
+            seen7 = False
+            for _ in range(400):
+                seq, st = q.get(timeout=180)
+                assert seq[0].state.shape == (17, 9, 9) and seq[0].pi_prob.shape == (81,) and seq[0].pi_prob.dtype == np.float32
+                assert st['game_result'] in ('B+1.0', 'W+1.0', 'DRAW') and 'num_passes' not in st
+                if st['training_steps'] == 7:
+                    seen7 = True
+                    break
+            assert seen7
+        finally:
+            stop.set()
+            for _ in range(200):  # drain so the child's blocking put can finish
+                try:
+                    q.get(timeout=0.5)
+                except Exception:
+                    break
+            p.join(timeout=120)
+            if p.is_alive():
+                p.terminate()
+    assert os.path.exists(tmp_path / 'actor3.csv')
