@@ -11,28 +11,35 @@
 #pragma once
 #include "az_state.h"
 #include "az_warp.cuh"
+#if defined(AZ_EMU) && defined(AZ_CHECK_LABELS)
+#include <stdio.h>
+#include <stdlib.h>
+#endif
 
 struct Sim {
   int8_t* board;    // [ncp]
   int8_t* ring;     // [8][ncp]  ring[(head+k)&7] = k-th most recent board
   int16_t* label;   // [ncp]
+  int16_t* root_label; // [ncp] group labels of the slot's real position, computed once per kernel and copied per descent
   int32_t* aux;     // [ncp]     liberties per group label / border flags per empty region
   uint8_t* legal;   // [Ap]
   uint8_t* nbm;     // [ncp] neighbour mask per cell: bit0 down (+n), bit1 up (-n), bit2 right (+1), bit3 left (-1)
   int32_t* path_k;  // [AZ_PATH] flat stats index (parent*Ap+move) of every node on the current descent
   int16_t* path_n;  // [AZ_PATH] node ids
   int to_play, steps, h1, h2, ko, head;
-  int labels_valid; // label[] / aux[] describe the stone groups of the current board
+  int labels_valid; // label[] describes the stone groups of the current board
+  int libs_valid;   // aux[] holds their liberty counts
   int caps_b, caps_w;
 };
 
-AZ_DEV size_t sim_bytes(const AzDims& d) { return (size_t)d.ncp * 16 + d.Ap + AZ_PATH * 6; }
+AZ_DEV size_t sim_bytes(const AzDims& d) { return (size_t)d.ncp * 18 + d.Ap + AZ_PATH * 6; }
 
 AZ_DEV void sim_carve(const AzDims& d, Sim& S, unsigned char* mem) {
   S.path_k = (int32_t*)mem; mem += AZ_PATH * 4;
   S.aux = (int32_t*)mem;  mem += (size_t)d.ncp * 4;
   S.label = (int16_t*)mem; mem += (size_t)d.ncp * 2;
   S.path_n = (int16_t*)mem; mem += AZ_PATH * 2;
+  S.root_label = (int16_t*)mem; mem += (size_t)d.ncp * 2;
   S.board = (int8_t*)mem;  mem += d.ncp;
   S.ring = (int8_t*)mem;   mem += (size_t)d.ncp * 8;
   S.legal = (uint8_t*)mem; mem += d.Ap;
@@ -78,6 +85,7 @@ AZ_DEV void sim_load(const AzState& E, int g, Sim& S) {
   S.caps_w = ei[EI_CAPS_W];
   S.head = 0;
   S.labels_valid = 0;
+  S.libs_valid = 0;
   w_sync();
 }
 
@@ -147,6 +155,7 @@ AZ_DEV void go_count_liberties(const AzDims& d, Sim& S) {
       }
     })
   }
+  S.libs_valid = 1;
   w_sync();
 }
 
@@ -165,9 +174,10 @@ AZ_DEV bool go_is_suicide(const AzDims& d, const Sim& S, int c, int colour) {
 AZ_DEV void go_legal(const AzDims& d, Sim& S) {
   if (!S.labels_valid) {
     go_label(d, S, false);
-    go_count_liberties(d, S);
     S.labels_valid = 1;
+    S.libs_valid = 0;
   }
+  if (!S.libs_valid) go_count_liberties(d, S);
   W_FOR(a, d.Ap) {
     uint8_t ok = 0;
     if (a < d.nc) ok = (S.board[a] == 0 && a != S.ko && !go_is_suicide(d, S, a, S.to_play)) ? 1 : 0;
@@ -181,6 +191,7 @@ AZ_DEV void go_legal(const AzDims& d, Sim& S) {
 AZ_DEV float go_score(const AzDims& d, Sim& S) {
   go_label(d, S, true);
   S.labels_valid = 0;
+  S.libs_valid = 0;
   W_FOR(c, d.nc) S.aux[c] = 0;
   w_sync();
   W_FOR(c, d.nc) {
@@ -231,7 +242,37 @@ AZ_DEV StepOut go_play(const AzDims& d, Sim& S, int action) {
     w_sync();
     W_LANE0 S.board[p] = (int8_t)mover;
     w_sync();
-    go_label(d, S, false);
+    if (!S.labels_valid) {
+      go_label(d, S, false);
+    } else {
+      // incremental: the new stone joins its friendly neighbour groups and the union keeps the smallest label
+      // (labels are "lowest cell index of the group", so this is exactly what a full relabel would produce)
+      int fl[4];
+      int nf = 0, newl = p;
+      AZ_NEIGHBOURS(d, p, q, {
+        if (S.board[q] == mover) {
+          const int l = S.label[q];
+          bool dup = false;
+          for (int t = 0; t < nf; ++t) dup = dup || (fl[t] == l);
+          if (!dup) { fl[nf++] = l; if (l < newl) newl = l; }
+        }
+      })
+      w_sync();
+      if (nf == 0) {
+        W_LANE0 S.label[p] = (int16_t)p;
+      } else {
+        W_FOR(c, d.nc) {
+          if (c == p) S.label[c] = (int16_t)newl;
+          else if (S.board[c] == mover) {
+            const int l = S.label[c];
+            bool hit = false;
+            for (int t = 0; t < nf; ++t) hit = hit || (fl[t] == l);
+            if (hit) S.label[c] = (int16_t)newl;
+          }
+        }
+      }
+      w_sync();
+    }
     go_count_liberties(d, S);
     int capl[4];
     int ncapl = 0;
@@ -253,7 +294,7 @@ AZ_DEV StepOut go_play(const AzDims& d, Sim& S, int action) {
           int l = S.label[c];
           bool hit = false;
           for (int t = 0; t < ncapl; ++t) hit = hit || (capl[t] == l);
-          if (hit) { S.board[c] = 0; cnt++; capcell = c; }
+          if (hit) { S.board[c] = 0; S.label[c] = -1; cnt++; capcell = c; }
         }
       }
       w_sync();
@@ -262,6 +303,14 @@ AZ_DEV StepOut go_play(const AzDims& d, Sim& S, int action) {
       go_count_liberties(d, S);  // surviving groups keep their labels; only liberties changed
     }
     S.labels_valid = 1;
+#if defined(AZ_EMU) && defined(AZ_CHECK_LABELS)
+    {  // test-only cross-check of the incremental labels against a full relabel
+      int16_t keep[512];
+      memcpy(keep, S.label, (size_t)d.nc * 2);
+      go_label(d, S, false);
+      if (memcmp(keep, S.label, (size_t)d.nc * 2) != 0) { fprintf(stderr, "incremental group labels diverged\n"); abort(); }
+    }
+#endif
     S.ko = (cnt == 1 && koish == -mover) ? capcell : -1;  // go_engine.py:491-494
     if (mover == 1) S.caps_b += cnt; else S.caps_w += cnt;
     o.captured = cnt;
@@ -359,7 +408,7 @@ AZ_DEV void env_reset(const AzState& E, int g, Sim& S) {
   const AzDims& d = E.d;
   W_FOR(c, d.ncp) S.board[c] = 0;
   for (int k = 0; k < 8; ++k) W_FOR(c, d.ncp) S.ring[k * d.ncp + c] = 0;
-  S.to_play = 1; S.steps = 0; S.h1 = -2; S.h2 = -2; S.ko = -1; S.head = 0; S.labels_valid = 0;
+  S.to_play = 1; S.steps = 0; S.h1 = -2; S.h2 = -2; S.ko = -1; S.head = 0; S.labels_valid = 0; S.libs_valid = 0;
   S.caps_b = S.caps_w = 0;
   w_sync();
   sim_legal(d, S);

@@ -29,7 +29,7 @@ static inline unsigned char* az_emu_scratch(size_t bytes) {
 #define AZ_THREAD_LOOP(i, n)                                                              \
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)(n); \
        i += (long long)gridDim.x * blockDim.x)
-static __host__ __device__ inline size_t az_sim_stride(const AzDims& d) { return ((size_t)d.ncp * 16 + d.Ap + AZ_PATH * 6 + 15) & ~(size_t)15; }
+static __host__ __device__ inline size_t az_sim_stride(const AzDims& d) { return ((size_t)d.ncp * 18 + d.Ap + AZ_PATH * 6 + 15) & ~(size_t)15; }
 #define AZ_SCRATCH(d, S)                                        \
   extern __shared__ __align__(16) unsigned char az_smem[];      \
   sim_carve((d), (S), az_smem + (threadIdx.x >> 5) * az_sim_stride(d))

@@ -17,6 +17,7 @@
 //   AZ_NET_BF16  az_net_tc.cu: tcgen05.mma (bf16 x bf16 -> f32 in TMEM), TMA-staged operands.
 #include <math.h>
 
+#include <thread>
 #include <vector>
 
 #include "az_net.h"
@@ -99,6 +100,16 @@ static float* upload(AzRt& rt, std::vector<void*>& allocs, const std::vector<flo
   allocs.push_back(p);
   rt_h2d(rt, p, v.data(), v.size() * sizeof(float));
   return p;
+}
+
+// allocate on first use, refresh in place afterwards
+static void dev_set(AzRt& rt, std::vector<void*>& allocs, float*& slot, const std::vector<float>& v) {
+  if (!slot) {
+    slot = (float*)rt_alloc(v.size() * sizeof(float));
+    if (!slot) return;
+    allocs.push_back(slot);
+  }
+  rt_h2d(rt, slot, v.data(), v.size() * sizeof(float));
 }
 
 AzNet* aznet_create(const AzDims& d, const az_config& cfg, AzRt& rt, int max_leaves, std::string& err) {
@@ -194,28 +205,45 @@ int aznet_set_weights(AzNet* n, AzRt& rt, const float* const* T, const int64_t* 
             " (AlphaZeroNet geometry mismatch)";
       return AZ_ERR_BAD_ARG;
     }
-  for (void* p : n->allocs) rt_free(p);
-  n->allocs.clear();
-  n->conv_w.clear();
-  n->conv_b.clear();
-  n->host_w.clear();
-  n->host_b.clear();
-  std::vector<float> wf, bf;
+  // device buffers are allocated on the first call and refreshed in place afterwards (checkpoint hot-swap path)
+  const int n_conv = 1 + 2 * nb;
+  if ((int)n->conv_w.size() != n_conv) {
+    n->conv_w.assign(n_conv, nullptr);
+    n->conv_b.assign(n_conv, nullptr);
+  }
+  n->host_w.assign(n_conv, std::vector<float>());
+  n->host_b.assign(n_conv, std::vector<float>());
+  n->layer_src.assign(n_conv, nullptr);
+  n->layer_cin.assign(n_conv, 0);
   int ti = 0;
-  fold_conv3(T[0], T[1], T[2], T[3], T[4], C, planes, n->g.cin_pad, wf, bf);
-  ti = 5;
-  n->host_w.push_back(wf);
-  n->host_b.push_back(bf);
-  for (int b = 0; b < nb; ++b)
-    for (int h = 0; h < 2; ++h) {
-      fold_conv3(T[ti], T[ti + 1], T[ti + 2], T[ti + 3], T[ti + 4], C, C, C, wf, bf);
-      ti += 5;
-      n->host_w.push_back(wf);
-      n->host_b.push_back(bf);
-    }
-  for (size_t i = 0; i < n->host_w.size(); ++i) {
-    n->conv_b.push_back(upload(rt, n->allocs, n->host_b[i]));
-    n->conv_w.push_back(n->precision == AZ_NET_FP32 ? upload(rt, n->allocs, n->host_w[i]) : nullptr);
+  for (int li = 0; li < n_conv; ++li) {
+    n->layer_src[li] = T + ti;   // {conv weight, bn gamma, beta, running_mean, running_var}
+    n->layer_cin[li] = li == 0 ? planes : C;
+    ti += 5;
+  }
+  {
+    // BatchNorm folding, one task per layer on a few host threads (the fp32 tap-major copy is only built for the parity tower)
+    const bool need_f32 = n->precision == AZ_NET_FP32;
+    auto work = [&](int t0, int step) {
+      for (int li = t0; li < n_conv; li += step) {
+        const float* const* L = n->layer_src[li];
+        const int cin = n->layer_cin[li], cin_pad = li == 0 ? n->g.cin_pad : C;
+        if (need_f32) fold_conv3(L[0], L[1], L[2], L[3], L[4], C, cin, cin_pad, n->host_w[li], n->host_b[li]);
+        else {
+          n->host_b[li].assign(C, 0.f);
+          for (int co = 0; co < C; ++co) n->host_b[li][co] = L[2][co] - L[3][co] * (L[1][co] / sqrtf(L[4][co] + 1e-5f));
+        }
+      }
+    };
+    const int nthreads = std::min(8, n_conv);
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; ++t) pool.emplace_back(work, t, nthreads);
+    work(0, nthreads);
+    for (auto& th : pool) th.join();
+  }
+  for (int li = 0; li < n_conv; ++li) {
+    dev_set(rt, n->allocs, n->conv_b[li], n->host_b[li]);
+    if (n->precision == AZ_NET_FP32) dev_set(rt, n->allocs, n->conv_w[li], n->host_w[li]);
   }
   // heads: 1x1 conv + BN folded
   std::vector<float> pw(2 * C), pb(2), vw(C), vb(1);
@@ -235,26 +263,17 @@ int aznet_set_weights(AzNet* n, AzRt& rt, const float* const* T, const int64_t* 
   ti += 5;
   std::vector<float> v1w(T[ti], T[ti] + (size_t)fc * HW), v1b(T[ti + 1], T[ti + 1] + fc), v2w(T[ti + 2], T[ti + 2] + fc),
       v2b(T[ti + 3], T[ti + 3] + 1);
+  std::vector<float> pfwT((size_t)2 * HW * A), v1wT((size_t)HW * fc);
+  for (int a2 = 0; a2 < A; ++a2)
+    for (int k = 0; k < 2 * HW; ++k) pfwT[(size_t)k * A + a2] = pfw[(size_t)a2 * 2 * HW + k];
+  for (int j = 0; j < fc; ++j)
+    for (int k = 0; k < HW; ++k) v1wT[(size_t)k * fc + j] = v1w[(size_t)j * HW + k];
+  const std::vector<float>* hv[12] = {&pw, &pb, &pfw, &pfb, &pfwT, &v1wT, &vw, &vb, &v1w, &v1b, &v2w, &v2b};
+  for (int i = 0; i < 12; ++i) dev_set(rt, n->allocs, n->head_dev[i], *hv[i]);
   HeadParams& hp = n->hp;
-  hp.pol_w = upload(rt, n->allocs, pw);
-  hp.pol_b = upload(rt, n->allocs, pb);
-  hp.pol_fc_w = upload(rt, n->allocs, pfw);
-  {
-    std::vector<float> t((size_t)2 * HW * A), u((size_t)HW * fc);
-    for (int a2 = 0; a2 < A; ++a2)
-      for (int k = 0; k < 2 * HW; ++k) t[(size_t)k * A + a2] = pfw[(size_t)a2 * 2 * HW + k];
-    for (int j = 0; j < fc; ++j)
-      for (int k = 0; k < HW; ++k) u[(size_t)k * fc + j] = v1w[(size_t)j * HW + k];
-    hp.pol_fc_wT = upload(rt, n->allocs, t);
-    hp.val_fc1_wT = upload(rt, n->allocs, u);
-  }
-  hp.pol_fc_b = upload(rt, n->allocs, pfb);
-  hp.val_w = upload(rt, n->allocs, vw);
-  hp.val_b = upload(rt, n->allocs, vb);
-  hp.val_fc1_w = upload(rt, n->allocs, v1w);
-  hp.val_fc1_b = upload(rt, n->allocs, v1b);
-  hp.val_fc2_w = upload(rt, n->allocs, v2w);
-  hp.val_fc2_b = upload(rt, n->allocs, v2b);
+  hp.pol_w = n->head_dev[0]; hp.pol_b = n->head_dev[1]; hp.pol_fc_w = n->head_dev[2]; hp.pol_fc_b = n->head_dev[3];
+  hp.pol_fc_wT = n->head_dev[4]; hp.val_fc1_wT = n->head_dev[5]; hp.val_w = n->head_dev[6]; hp.val_b = n->head_dev[7];
+  hp.val_fc1_w = n->head_dev[8]; hp.val_fc1_b = n->head_dev[9]; hp.val_fc2_w = n->head_dev[10]; hp.val_fc2_b = n->head_dev[11];
   if (!hp.val_fc2_b) { err = "out of device memory"; return AZ_ERR_CUDA; }
   if (n->precision == AZ_NET_BF16) {
     int rc = aznet_tc_set_weights(n, rt, err);

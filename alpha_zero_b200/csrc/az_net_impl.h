@@ -35,6 +35,9 @@ struct AzNet {
   std::vector<float*> conv_w, conv_b;                // device, fp32 tower: [9][cin_pad][cout], [cout]
   std::vector<std::vector<float>> host_w, host_b;    // folded host copies (source for the bf16 packing)
   HeadParams hp;
+  float* head_dev[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::vector<const float* const*> layer_src;  // per conv layer: {weight, gamma, beta, mean, var} (valid during az_set_weights)
+  std::vector<int> layer_cin;
   std::vector<void*> allocs;
   double flops = 0.0;
   AzNetTc* tc = nullptr;

@@ -17,6 +17,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <thread>
 
 #include "az_net_impl.h"
 #include "az_net_kernels.cuh"
@@ -682,34 +683,49 @@ void aznet_tc_destroy(AzNet* n) {
   n->tc = nullptr;
 }
 
-// Pack folded fp32 weights [9][cin_pad][cout] into bf16 [9][cout][cin] (K-major B operand) and build their TMA maps.
+// Fold BatchNorm and pack straight into bf16 [9][cout][cin] (K-major B operand), one host thread per group of layers;
+// device buffers and TMA maps are created on the first call and refreshed in place afterwards.
 int aznet_tc_set_weights(AzNet* n, AzRt& rt, std::string& err) {
   AzNetTc* tc = n->tc;
-  for (auto* p : tc->w_dev) rt_free(p);
-  tc->w_dev.clear();
-  tc->map_w.clear();
-  tc->map_w_half.clear();
   const int C = n->C;
-  for (size_t li = 0; li < n->host_w.size(); ++li) {
-    const int cin_src = li == 0 ? n->g.cin_pad : C;  // layer 0 was folded with the input rows' channel padding (64 here)
+  const int n_conv = (int)n->layer_src.size();
+  std::vector<std::vector<__nv_bfloat16>> pk(n_conv);
+  auto work = [&](int t0, int step) {
+    for (int li = t0; li < n_conv; li += step) {
+      const float* const* L = n->layer_src[li];
+      const int cin_src = n->layer_cin[li], cin = li == 0 ? 64 : C;
+      pk[li].assign((size_t)9 * C * cin, __float2bfloat16(0.f));
+      for (int co = 0; co < C; ++co) {
+        const float sc = L[1][co] / sqrtf(L[4][co] + 1e-5f);
+        for (int ci = 0; ci < cin_src; ++ci) {
+          const float* w9 = L[0] + ((size_t)co * cin_src + ci) * 9;
+          for (int t = 0; t < 9; ++t) pk[li][((size_t)t * C + co) * cin + ci] = __float2bfloat16(w9[t] * sc);
+        }
+      }
+    }
+  };
+  {
+    const int nthreads = std::min(8, n_conv);
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; ++t) pool.emplace_back(work, t, nthreads);
+    work(0, nthreads);
+    for (auto& th : pool) th.join();
+  }
+  const bool first = tc->w_dev.empty();
+  for (int li = 0; li < n_conv; ++li) {
     const int cin = li == 0 ? 64 : C;
-    const std::vector<float>& w = n->host_w[li];
-    std::vector<__nv_bfloat16> pk((size_t)9 * C * cin, __float2bfloat16(0.f));
-    for (int t = 0; t < 9; ++t)
-      for (int ci = 0; ci < cin_src; ++ci)
-        for (int co = 0; co < C; ++co) pk[((size_t)t * C + co) * cin + ci] = __float2bfloat16(w[((size_t)t * cin_src + ci) * C + co]);
-    __nv_bfloat16* d = (__nv_bfloat16*)rt_alloc(pk.size() * 2);
-    if (!d) { err = "out of device memory"; return AZ_ERR_CUDA; }
-    rt_h2d(rt, d, pk.data(), pk.size() * 2);
-    tc->w_dev.push_back(d);
-    CUtensorMap m;
-    int rc = make_map(&m, d, (uint64_t)cin, (uint64_t)9 * C, (uint32_t)C, err);
-    if (rc) return rc;
-    tc->map_w.push_back(m);
-    CUtensorMap mh;
-    rc = make_map(&mh, d, (uint64_t)cin, (uint64_t)9 * C, (uint32_t)(C / 2), err);
-    if (rc) return rc;
-    tc->map_w_half.push_back(mh);
+    if (first) {
+      __nv_bfloat16* d = (__nv_bfloat16*)rt_alloc(pk[li].size() * 2);
+      if (!d) { err = "out of device memory"; return AZ_ERR_CUDA; }
+      tc->w_dev.push_back(d);
+      CUtensorMap m, mh;
+      int rc = make_map(&m, d, (uint64_t)cin, (uint64_t)9 * C, (uint32_t)C, err);
+      if (!rc) rc = make_map(&mh, d, (uint64_t)cin, (uint64_t)9 * C, (uint32_t)(C / 2), err);
+      if (rc) return rc;
+      tc->map_w.push_back(m);
+      tc->map_w_half.push_back(mh);
+    }
+    rt_h2d(rt, tc->w_dev[li], pk[li].data(), pk[li].size() * 2);
   }
   return 0;
 }

@@ -331,9 +331,20 @@ AZ_DEV void game_collect(const AzState& E, int g, Sim& S, LocalCounters& lc) {
       TreeView T = tree_view(E, g, ti[TI_BUF]);
       int n_nodes = ti[TI_NODES];
       int tries = 0;
+      if (d.game == 0) {  // group labels of the root position: one full labelling per pass, copied into every descent
+        sim_load(E, g, S);
+        go_label(d, S, false);
+        W_FOR(c, d.nc) S.root_label[c] = S.label[c];
+        w_sync();
+      }
       while (nleaves < E.s.P && tries < E.s.tries) {
         tries++;
         sim_load(E, g, S);
+        if (d.game == 0) {
+          W_FOR(c, d.nc) S.label[c] = S.root_label[c];
+          S.labels_valid = 1;
+          w_sync();
+        }
         int node = 0, depth = 0;
         float n_cur = 0.f;
         bool expanded_cur = true;  // the root of a running search is always expanded

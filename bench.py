@@ -100,22 +100,21 @@ def cpu_worker(args):
     """One reference-style actor: the oracle's restatement of play_and_record_one_game (pipeline.py:289-382),
     single-threaded torch CPU net, until the time budget is spent.  Returns (simulations, moves, seconds)."""
     seed, seconds, wl = args
-    os.environ['OMP_NUM_THREADS'] = '1'
-    os.environ['MKL_NUM_THREADS'] = '1'
     import numpy as np
-    import torch
 
-    torch.set_num_threads(1)
-    from oracle import net as onet
     from oracle.boards import GoBoard, GomokuBoard
     from oracle.search import search
 
     game, n, _, sims, par, nb, nf, fc, warm, _ = WORKLOADS[wl]
-    sd = make_net(game, n, nb, nf, fc).state_dict()
-    ev = onet.make_eval_func(sd, game == 'gomoku')
-    np.random.seed(seed)
-    env = GoBoard(n) if game == 'go' else GomokuBoard(n)
-    root, total, moves = None, 0.0, 0
+    if 'ev' not in _CPU_STATE:
+        _cpu_init(wl)
+    ev = _CPU_STATE['ev']
+    if _CPU_STATE.get('env') is None:
+        np.random.seed(seed)
+        _CPU_STATE['env'] = GoBoard(n) if game == 'go' else GomokuBoard(n)
+        _CPU_STATE['root'] = None
+    env, root = _CPU_STATE['env'], _CPU_STATE['root']
+    total, moves = 0.0, 0
     t0 = time.time()
     while time.time() - t0 < seconds:
         if env.is_game_over():
@@ -126,20 +125,54 @@ def cpu_worker(args):
         total += float(child_N.sum()) + 1.0 - before
         moves += 1
         env.step(mv)
+    _CPU_STATE['root'] = root
     return total, moves, time.time() - t0
 
 
-def run_cpu(wl, seconds, cores=None):
-    import multiprocessing as mp
+_CPU_STATE = {}
 
-    cores = cores or os.cpu_count() or 1
-    ctx = mp.get_context('spawn')
-    with ctx.Pool(cores) as pool:
-        res = pool.map(cpu_worker, [(1 + i, seconds, wl) for i in range(cores)])
-    sims = sum(r[0] for r in res)
-    moves = sum(r[1] for r in res)
-    wall = max(r[2] for r in res)
-    return sims / wall, moves / wall, cores, wall
+
+def _cpu_init(wl):
+    """Per-process setup of a reference-style actor: single-threaded torch, the workload's network, the oracle evaluator."""
+    os.environ['OMP_NUM_THREADS'] = '1'
+    os.environ['MKL_NUM_THREADS'] = '1'
+    import torch
+
+    torch.set_num_threads(1)
+    from oracle import net as onet
+
+    game, n, _, sims, par, nb, nf, fc, warm, _ = WORKLOADS[wl]
+    _CPU_STATE['ev'] = onet.make_eval_func(make_net(game, n, nb, nf, fc).state_dict(), game == 'gomoku')
+    _CPU_STATE['env'] = None
+
+
+class CpuPool:
+    """One pool of actor processes for the whole run (process start + torch import are paid once, outside the timed samples)."""
+
+    def __init__(self, wl, cores=None):
+        import multiprocessing as mp
+
+        self.wl = wl
+        self.cores = cores or os.cpu_count() or 1
+        self.pool = mp.get_context('spawn').Pool(self.cores, initializer=_cpu_init, initargs=(wl,))
+
+    def run(self, seconds):
+        res = self.pool.map(cpu_worker, [(1 + i, seconds, self.wl) for i in range(self.cores)])
+        wall = max(r[2] for r in res)
+        return sum(r[0] for r in res) / wall, sum(r[1] for r in res) / wall, self.cores, wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def run_cpu(wl, seconds, cores=None):
+    pool = CpuPool(wl, cores)
+    try:
+        pool.run(1.0)  # untimed: first-touch of the conv kernels in every process
+        return pool.run(seconds)
+    finally:
+        pool.close()
 
 
 def reference_arm(a):
@@ -149,14 +182,16 @@ def reference_arm(a):
     if rank != 0:
         return
     per_step = float(os.environ.get('AZ_REF_SECONDS', '12'))
-    for _ in range(a.warmup):
-        run_cpu(a.workload, 2.0)
+    pool = CpuPool(a.workload)
+    for _ in range(max(1, a.warmup)):
+        pool.run(1.5)
     vals, mv = [], []
     t0 = time.time()
     for _ in range(a.steps):
-        s, m, cores, wall = run_cpu(a.workload, per_step)
+        s, m, cores, wall = pool.run(per_step)
         vals.append(s)
         mv.append(m)
+    pool.close()
     v = sum(vals) / len(vals)
     game, n, G, sims, par, nb, nf, fc, _, _ = WORKLOADS[a.workload]
     line = {
@@ -301,6 +336,12 @@ def main():
         peak = peaks.get('bf16_tflops_sustained') if a.precision == 'bf16' else None
         peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peak else 'fallback 1400 TF/s (of fallback)'
         peak = peak or 1400.0
+        # DRAM traffic of the dominant kernel per launch: from the committed `ncu --set full` capture (profiles/
+        # r01_ncu_k_conv_tc_halo_pair_raw.csv, 16384 leaves: dram read+write 1209.1 MB with / 790.0 MB without the residual add),
+        # mean over the tower's 10 residual + 11 plain launches, scaled linearly to this tick's leaf count
+        traffic = None
+        if a.workload == 'go9_c2' and a.precision == 'bf16' and os.environ.get('AZ_TC_MODE', '4') == '4':
+            traffic = (10 * 1209.1e6 + 11 * 790.0e6) / 21 * (tower_evals / 16384.0)
         value = d['simulations'] / (ms_max * 1e-3)
         line = {
             'metric': 'mcts_simulations_per_sec', 'value': value, 'unit': 'simulations/s', 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
@@ -315,7 +356,8 @@ def main():
                     'd2h_bytes_per_step': int(d2h_bytes / max(1, a.steps)), 'samples_all_gathered': gathered},
             'gpu_launches': int(launches),
             'roofline': {'bound': 'tensor', 'kernel': ('k_conv_tc_halo' if nf <= 128 and os.environ.get('AZ_TC_MODE', '2') != '0' else 'k_conv_tc') if a.precision == 'bf16' else 'k_conv_f32', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                         'frac': (achieved / peak) if achieved else None, 'traffic': None, 'peak_source': peak_src,
+                         'frac': (achieved / peak) if achieved else None, 'traffic': traffic, 'traffic_unit': 'bytes per launch (ncu dram__bytes_read+write)',
+                         'algorithmic_bytes_per_launch': 2.0 * tower_evals * (n * n if game == 'go' else (n + 4) ** 2) * nf * 2, 'peak_source': peak_src,
                          'note': f'algorithmic 2*MAC of one 3x3 conv layer ({conv_flops_per_eval / 1e6:.1f} MFLOP/leaf) x {tower_evals} leaves / mean launch time over the '
                                  f'{n_conv} tower launches of the last tick ({tower_ms:.3f} ms, CUDA events on the engine stream)'},
             'clocks': clk.summary(),
