@@ -115,7 +115,8 @@ AZ_DEV void sim_write_obs(const AzDims& d, const Sim& S, int8_t* out) {
 }
 
 // Min-label propagation with pointer jumping: label[c] = lowest cell index of the connected set of
-// equal-valued cells containing c.  Stones always; empty regions only when with_empty.
+// equal-valued cells containing c.  Stones always; empty regions only when with_empty.  Jacobi style (all
+// lanes read label[], write aux[], then copy back) so that no lane reads a cell another lane is writing.
 AZ_DEV void go_label(const AzDims& d, Sim& S, bool with_empty) {
   W_FOR(c, d.nc) S.label[c] = (S.board[c] != 0 || with_empty) ? (int16_t)c : (int16_t)-1;
   w_sync();
@@ -123,17 +124,21 @@ AZ_DEV void go_label(const AzDims& d, Sim& S, bool with_empty) {
   do {
     changed = false;
     W_FOR(c, d.nc) {
-      int l = S.label[c];
-      if (l < 0) continue;
-      int8_t v = S.board[c];
+      const int l = S.label[c];
       int m = l;
-      AZ_NEIGHBOURS(d, c, q, {
-        if (S.board[q] == v) { int lq = S.label[q]; if (lq < m) m = lq; }
-      })
-      int lm = S.label[m];
-      if (lm < m) m = lm;
-      if (m < l) { S.label[c] = (int16_t)m; changed = true; }
+      if (l >= 0) {
+        const int8_t v = S.board[c];
+        AZ_NEIGHBOURS(d, c, q, {
+          if (S.board[q] == v) { const int lq = S.label[q]; if (lq < m) m = lq; }
+        })
+        const int lm = S.label[m];
+        if (lm < m) m = lm;
+        if (m < l) changed = true;
+      }
+      S.aux[c] = m;
     }
+    w_sync();
+    W_FOR(c, d.nc) S.label[c] = (int16_t)S.aux[c];
     w_sync();
   } while (w_any(changed));
 }

@@ -193,7 +193,7 @@ class Engine:
         return {k: int(getattr(c, k)) for k, _ in AzCounters._fields_}
 
     def drain_games(self, max_games=4096, max_samples=None):
-        max_samples = max_samples or int(self.cfg.sample_ring)
+        max_samples = max_samples or min(int(self.cfg.sample_ring), 262144)  # more finished samples stay queued for the next call
         recs = (AzGameRecord * max_games)()
         st = np.empty((max_samples, self.obs_bytes), dtype=np.int8)
         pis = np.empty((max_samples, self.A), dtype=np.float32)

@@ -201,3 +201,49 @@ def _check_games(games, states, zs):
         else:
             black_z = 1.0 if g['winner'] == 1 else -1.0
             np.testing.assert_array_equal(zz, np.where(colour == 1, black_z, -black_z))
+
+
+def test_selfplay_device_rng_statistics(cuda):
+    """The device-resident loop draws its Dirichlet noise and samples its moves from a counter-based generator, so it cannot
+    be bit-compared with a numpy-seeded run.  Distribution-level check against the oracle game loop (same net, same settings):
+    the mean search policy of the opening move (an average over root-noise draws) within 0.03 per action, the opening-move
+    histogram within 0.08 total-variation... loose bounds sized for 512 device / 96 oracle games."""
+    from alpha_zero_b200.engine import Engine
+    from oracle import net as onet
+    from oracle.boards import GoBoard
+    from oracle.selfplay import play_one_game
+
+    z, n, a, nb, nf, fc, gomoku, net = _net_case('go9_small')
+    sd = net.state_dict()
+    sims, par, max_steps = 32, 4, 12
+    eng = Engine('go', 9, num_games=512, max_simulations=sims, max_parallel=par, net=(nb, nf, fc), precision='fp32', max_steps=max_steps, seed=11)
+    eng.set_weights(sd)
+    eng.selfplay_begin(sims, par, warm_up_steps=100, check_resign_after_steps=100, resign_threshold=-1.0, disable_resign_ratio=1.0)
+    dev_pi, dev_first, dev_len = [], [], []
+    while len(dev_pi) < 512:
+        eng.selfplay_tick(12)
+        games, states, pis, zs = eng.drain_games()
+        mv = eng.last_moves
+        for g in games:
+            dev_pi.append(pis[g['first_sample']])
+            dev_first.append(int(mv[g['first_sample']]))
+            dev_len.append(g['game_length'])
+    assert eng.counters()['errors'] == 0
+    eng.close()
+    ev = onet.make_eval_func(sd, False)
+    np.random.seed(3)
+    ora_pi, ora_first, ora_len = [], [], []
+    for _ in range(96):
+        env = GoBoard(9, 7.5, 8, max_steps)
+        seq, stats = play_one_game(env, ev, sims, par, True, 19652.0, 1.25, 100, 100, -1.0)
+        ora_pi.append(np.asarray(seq[0][1], dtype=np.float64))
+        ora_first.append(env.history[0])
+        ora_len.append(stats['game_length'])
+    dp, op = np.mean(dev_pi[:512], axis=0), np.mean(ora_pi, axis=0)
+    assert np.abs(dp - op).max() < 0.03, np.abs(dp - op).max()
+    hd = np.bincount(dev_first[:512], minlength=82) / 512.0
+    # the opening move is sampled from pi (T = 1 in warm-up, pass excluded): its histogram must follow the mean policy
+    exp = dp.copy(); exp[81] = 0; exp /= exp.sum()
+    assert 0.5 * np.abs(hd - exp).sum() < 0.12, 0.5 * np.abs(hd - exp).sum()
+    assert hd[81] == 0 and all(f != 81 for f in ora_first)
+    assert abs(np.mean(dev_len) - np.mean(ora_len)) < 0.6
