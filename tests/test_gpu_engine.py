@@ -207,7 +207,7 @@ def test_selfplay_device_rng_statistics(cuda):
     """The device-resident loop draws its Dirichlet noise and samples its moves from a counter-based generator, so it cannot
     be bit-compared with a numpy-seeded run.  Distribution-level check against the oracle game loop (same net, same settings):
     the mean search policy of the opening move (an average over root-noise draws) within 0.03 per action, the opening-move
-    histogram within 0.08 total-variation... loose bounds sized for 512 device / 96 oracle games."""
+    histogram within twice the total variation expected from sampling noise (512 device / 96 oracle games)."""
     from alpha_zero_b200.engine import Engine
     from oracle import net as onet
     from oracle.boards import GoBoard
@@ -244,6 +244,9 @@ def test_selfplay_device_rng_statistics(cuda):
     hd = np.bincount(dev_first[:512], minlength=82) / 512.0
     # the opening move is sampled from pi (T = 1 in warm-up, pass excluded): its histogram must follow the mean policy
     exp = dp.copy(); exp[81] = 0; exp /= exp.sum()
-    assert 0.5 * np.abs(hd - exp).sum() < 0.12, 0.5 * np.abs(hd - exp).sum()
+    # sampling noise alone: E|h_i - p_i| ~ sqrt(2 p_i (1 - p_i) / (pi N)); allow twice the expected total variation
+    tv_expected = 0.5 * np.sqrt(2.0 * exp * (1.0 - exp) / (np.pi * 512)).sum()
+    tv = 0.5 * np.abs(hd - exp).sum()
+    assert tv < 2.0 * tv_expected + 0.02, (tv, tv_expected)
     assert hd[81] == 0 and all(f != 81 for f in ora_first)
     assert abs(np.mean(dev_len) - np.mean(ora_len)) < 0.6
