@@ -113,6 +113,20 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// issue only: the registers may be read after tc_wait_ld()
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const float* __restrict__ bias,
@@ -535,6 +549,8 @@ k_conv_tc_halo(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           }
           continue;
         }
+        uint32_t v[32];  // accumulator row segment of this lane: requested now, consumed after the residual staging below
+        tc_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * 2 + h) * L.cout + cc), v);
         if (L.has_res) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stage + (size_t)(i * 8 + crow) * srow + cchunk * 16) = pre[i];
@@ -554,8 +570,7 @@ k_conv_tc_halo(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const bool valid = (m < M) && yy < L.Hc && xx < L.Hc;
         unsigned char* myrow = stage + (size_t)lane * srow;
         {
-          uint32_t v[32];
-          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * 2 + h) * L.cout + cc), v);
+          tc_wait_ld();
           __align__(16) __nv_bfloat16 o[32];
           if (valid) {
             __align__(16) __nv_bfloat16 rr[32];
