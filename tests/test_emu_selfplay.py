@@ -1,0 +1,98 @@
+"""The device-resident self-play loop (csrc/az_tree.cuh: game_advance / game_new, rings, az_drain_games) on the host-emulation
+build with a hash evaluator standing in for the network: every finished game is replayed through the ORACLE board engine and
+must be a legal, correctly scored, correctly labelled game."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'emu'))
+import build_emu  # noqa: E402
+from alpha_zero_b200._lib import Binding  # noqa: E402
+from alpha_zero_b200.engine import Engine  # noqa: E402
+from oracle.boards import GoBoard, GomokuBoard  # noqa: E402
+
+
+@pytest.fixture(scope='module')
+def emu():
+    return Binding(ctypes.CDLL(build_emu.build()))
+
+
+def _dummy_weights(blocks, filters, fc, planes, A, hw):
+    shapes = [(filters * planes * 9,)] + [(filters,)] * 4
+    for _ in range(blocks * 2):
+        shapes += [(filters * filters * 9,)] + [(filters,)] * 4
+    shapes += [(2 * filters,)] + [(2,)] * 4 + [(A * 2 * hw,), (A,)] + [(filters,)] + [(1,)] * 4 + [(fc * hw,), (fc,), (fc,), (1,)]
+    return {f't{i}': np.zeros(s, dtype=np.float32) for i, s in enumerate(shapes)}
+
+
+def _check_game(game, rec, states, pis, zs, moves, max_steps):
+    env = GoBoard(9, 7.5, 8, max_steps) if game == 'go' else GomokuBoard(9, 5, 8)
+    ln = rec['game_length']
+    s0 = rec['first_sample']
+    black, white = env.black_player, env.white_player
+    obs = env.reset()
+    to_plays = []
+    reward, done = 0.0, False
+    for i in range(ln):
+        assert not done
+        np.testing.assert_array_equal(states[s0 + i], obs)
+        pi = pis[s0 + i]
+        assert abs(float(pi.sum()) - 1.0) < 1e-5
+        assert np.all(np.asarray(env.legal_actions)[pi > 0] == 1)  # the search policy lives on legal moves only
+        mv = int(moves[s0 + i])
+        to_plays.append(env.to_play)
+        if mv >= 0:
+            assert env.legal_actions[mv] == 1
+        obs, reward, done, _ = env.step(mv)
+    assert done
+    assert bool(rec['by_resign']) == (int(moves[s0 + ln - 1]) == -1)
+    assert (0 if env.winner is None else env.winner) == rec['winner']
+    if game == 'go':
+        assert rec['num_passes'] == sum(1 for i in range(ln) if int(moves[s0 + i]) == 81)
+        if not rec['by_resign']:
+            assert abs(env.score() - rec['score']) < 1e-6
+    z = zs[s0:s0 + ln]
+    if reward == 0.0:
+        assert np.all(z == 0)
+    else:  # pipeline.py:349-354
+        want = np.array([reward if p == env.last_player else -reward for p in to_plays], dtype=np.float32)
+        np.testing.assert_array_equal(z, want)
+    if rec['is_marked_for_resign']:
+        assert rec['is_resign_disabled'] and rec['marked_resign_player'] in (black, white)
+        assert bool(rec['is_could_won']) == (rec['winner'] == rec['marked_resign_player'])
+    if rec['by_resign']:
+        assert not rec['is_resign_disabled']
+    return ln
+
+
+@pytest.mark.parametrize('game', ['go', 'gomoku'])
+def test_selfplay_loop_produces_valid_games(emu, game):
+    A = 82 if game == 'go' else 81
+    max_steps = 36
+    eng = Engine(game, 9, num_games=12, max_simulations=16, max_parallel=4, net=(1, 16, 16), precision='fp32',
+                 max_steps=max_steps if game == 'go' else 0, seed=3, sample_ring=700, binding=emu)
+    eng.set_weights(_dummy_weights(1, 16, 16, 17, A, 81 if game == 'go' else 169))
+    eng.selfplay_begin(12, 4, warm_up_steps=6, check_resign_after_steps=8, resign_threshold=-0.55, disable_resign_ratio=0.5)
+    n_games, n_resign, n_marked, total = 0, 0, 0, 0
+    for rnd in range(60):
+        eng.selfplay_tick(8)
+        if rnd == 20:  # knobs can change while games are in flight (var_resign_threshold, pipeline.py:241-246)
+            eng.selfplay_update(6, 8, -0.5, 0.5)
+        games, states, pis, zs = eng.drain_games()
+        mv = eng.last_moves
+        for rec in games:
+            total += _check_game(game, rec, states, pis, zs, mv, max_steps)
+            n_games += 1
+            n_resign += rec['by_resign']
+            n_marked += rec['is_marked_for_resign']
+    c = eng.counters()
+    assert c['errors'] == 0 and c['ring_dropped'] == 0 and c['games'] == n_games and c['samples'] == total
+    assert n_games >= 12
+    if game == 'go':
+        assert n_resign > 0 and n_marked > 0  # both branches of the resignation logic were taken
+    else:
+        assert n_resign == 0
+    eng.close()

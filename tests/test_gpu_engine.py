@@ -183,6 +183,10 @@ def test_selfplay_device_loop(cuda):
         if len(games):
             np.testing.assert_allclose(pis.sum(axis=1), 1.0, atol=1e-5)
         _check_games(games, states, zs)
+        from test_emu_selfplay import _check_game  # replay every finished game through the oracle board engine
+
+        for rec in games:
+            _check_game('go', rec, states, pis, zs, eng.last_moves, 30)
     c = eng.counters()
     assert c['errors'] == 0 and c['games'] > 0 and c['moves'] > 64 and c['ring_dropped'] == 0, c
     assert total_games == c['games']
