@@ -32,6 +32,11 @@ struct az_engine {
   int last_total = 0;
   bool selfplay = false;
   unsigned long long drained_games = 0, dropped_samples = 0;
+  long long rp_samples_added = 0, rp_games_added = 0;  // UniformReplay.num_samples_added / num_games_added
+  int32_t* d_rp_idx = nullptr;
+  int8_t* d_rp_obs = nullptr;
+  float *d_rp_pi = nullptr, *d_rp_z = nullptr;
+  int rp_batch_cap = 0;
   float last_net_ms = 0.f;
   int last_net_evals = 0;
 #ifndef AZ_EMU
@@ -722,4 +727,119 @@ extern "C" int az_last_net_ms(az_engine* e, float* ms, int32_t* n_evals) {
   if (n_evals) *n_evals = 0;
 #endif
   return AZ_OK;
+}
+
+// ---- device-resident replay: the learner's input path -----------------------------------------
+// Mirrors UniformReplay (core/replay.py:35-116): circular storage, add_game / add, uniform sampling with replacement by
+// caller-supplied indices (so a numpy RandomState on the host reproduces the reference's minibatches), plus the batch-wide
+// dihedral transformation of utils/transformation.py:160 applied while gathering.
+extern "C" int az_replay_create(az_engine* e, int32_t capacity) {
+  if (!e || capacity <= 0) return az_fail(AZ_ERR_BAD_ARG, "Expect capacity to be a positive integer");
+  if (e->E.rp_obs) return az_fail(AZ_ERR_STATE, "replay already created");
+  const AzDims& d = e->E.d;
+  e->E.rp_obs = dev_alloc<int8_t>(e, (size_t)capacity * d.obs_bytes);
+  e->E.rp_pi = dev_alloc<float>(e, (size_t)capacity * d.A);
+  e->E.rp_z = dev_alloc<float>(e, capacity);
+  if (!e->E.rp_z) return az_fail(AZ_ERR_CUDA, "az_replay_create: device allocation failed");
+  e->E.rp_cap = capacity;
+  e->rp_samples_added = e->rp_games_added = 0;
+  return AZ_OK;
+}
+
+static void replay_copy_in(az_engine* e, const int8_t* so, const float* sp, const float* sz, size_t n, bool from_device) {
+  const AzDims& d = e->E.d;
+  size_t done = 0;
+  while (done < n) {  // circular: at most two segments per call unless n exceeds the capacity
+    const size_t pos = (size_t)(e->rp_samples_added % e->E.rp_cap);
+    const size_t m = std::min(n - done, (size_t)e->E.rp_cap - pos);
+    if (from_device) {
+      rt_d2d(e->rt, e->E.rp_obs + pos * d.obs_bytes, so + done * d.obs_bytes, m * d.obs_bytes);
+      rt_d2d(e->rt, e->E.rp_pi + pos * d.A, sp + done * d.A, m * d.A * sizeof(float));
+      rt_d2d(e->rt, e->E.rp_z + pos, sz + done, m * sizeof(float));
+    } else {
+      rt_h2d(e->rt, e->E.rp_obs + pos * d.obs_bytes, so + done * d.obs_bytes, m * d.obs_bytes);
+      rt_h2d(e->rt, e->E.rp_pi + pos * d.A, sp + done * d.A, m * d.A * sizeof(float));
+      rt_h2d(e->rt, e->E.rp_z + pos, sz + done, m * sizeof(float));
+    }
+    e->rp_samples_added += (long long)m;
+    done += m;
+  }
+}
+
+extern "C" int az_replay_add(az_engine* e, const int8_t* states, const float* pis, const float* values, int32_t n, int32_t n_games) {
+  if (!e || !e->E.rp_obs) return az_fail(AZ_ERR_STATE, "replay not created");
+  if (n < 0 || (n > 0 && (!states || !pis || !values))) return az_fail(AZ_ERR_BAD_ARG, "az_replay_add: bad arguments");
+  replay_copy_in(e, states, pis, values, (size_t)n, false);
+  e->rp_games_added += n_games;
+  return rt_sync(e->rt);
+}
+
+// Move every finished, not yet consumed game from the sample ring into the replay, device to device (add_game per game).
+extern "C" int az_replay_ingest(az_engine* e, int32_t* n_games, int32_t* n_samples) {
+  if (!e || !e->E.rp_obs) return az_fail(AZ_ERR_STATE, "replay not created");
+  const AzDims& d = e->E.d;
+  int rc = rt_sync(e->rt);
+  if (rc) return rc;
+  unsigned long long c[CT_COUNT];
+  rt_d2h(e->rt, c, e->E.counters, sizeof(c));
+  const unsigned long long head = c[CT_GAMES_HEAD];
+  if (head - e->drained_games > AZ_GAMES_RING) e->drained_games = head - AZ_GAMES_RING;
+  int ng = 0, ns = 0;
+  while (e->drained_games < head) {
+    int32_t gr[GR_INTS];
+    rt_d2h(e->rt, gr, e->E.games_ring + (size_t)(e->drained_games % AZ_GAMES_RING) * GR_INTS, sizeof(gr));
+    const int len = gr[GR_LEN];
+    const unsigned long long first = (unsigned long long)(uint32_t)gr[GR_FIRST_LO] | ((unsigned long long)(uint32_t)gr[GR_FIRST_HI] << 32);
+    e->drained_games++;
+    if (c[CT_RING_HEAD] - first > (unsigned long long)d.ring_cap) { e->dropped_samples += (unsigned long long)len; continue; }
+    const size_t s0 = (size_t)(first % (unsigned long long)d.ring_cap);
+    const size_t n1 = std::min((size_t)len, (size_t)d.ring_cap - s0), n2 = (size_t)len - n1;
+    replay_copy_in(e, e->E.r_obs + s0 * d.obs_bytes, e->E.r_pi + s0 * d.A, e->E.r_z + s0, n1, true);
+    if (n2) replay_copy_in(e, e->E.r_obs, e->E.r_pi, e->E.r_z, n2, true);
+    e->rp_games_added += 1;
+    ng++;
+    ns += len;
+  }
+  if (n_games) *n_games = ng;
+  if (n_samples) *n_samples = ns;
+  return rt_sync(e->rt);
+}
+
+extern "C" int az_replay_info(az_engine* e, int64_t* num_samples_added, int64_t* num_games_added, int32_t* size, int32_t* capacity) {
+  if (!e || !e->E.rp_obs) return az_fail(AZ_ERR_STATE, "replay not created");
+  if (num_samples_added) *num_samples_added = e->rp_samples_added;
+  if (num_games_added) *num_games_added = e->rp_games_added;
+  if (size) *size = (int32_t)std::min<long long>(e->rp_samples_added, e->E.rp_cap);
+  if (capacity) *capacity = e->E.rp_cap;
+  return AZ_OK;
+}
+
+extern "C" int az_replay_sample(az_engine* e, const int32_t* indices, int32_t batch, int32_t transform, int8_t* states, float* pis,
+                                float* values, int32_t outputs_on_device) {
+  if (!e || !e->E.rp_obs) return az_fail(AZ_ERR_STATE, "replay not created");
+  if (!indices || batch <= 0 || !states || !pis || !values) return az_fail(AZ_ERR_BAD_ARG, "az_replay_sample: bad arguments");
+  if (transform < 0 || transform > 5) return az_fail(AZ_ERR_BAD_ARG, "az_replay_sample: transform must be in [0, 5]");
+  const AzDims& d = e->E.d;
+  const int size = (int)std::min<long long>(e->rp_samples_added, e->E.rp_cap);
+  for (int i = 0; i < batch; ++i)
+    if (indices[i] < 0 || indices[i] >= size) return az_fail(AZ_ERR_BAD_ARG, "az_replay_sample: index out of range");
+  if (batch > e->rp_batch_cap) {  // staging grows with the largest batch seen
+    e->d_rp_idx = dev_alloc<int32_t>(e, batch);
+    e->d_rp_obs = dev_alloc<int8_t>(e, (size_t)batch * d.obs_bytes);
+    e->d_rp_pi = dev_alloc<float>(e, (size_t)batch * d.A);
+    e->d_rp_z = dev_alloc<float>(e, batch);
+    if (!e->d_rp_z) return az_fail(AZ_ERR_CUDA, "az_replay_sample: device allocation failed");
+    e->rp_batch_cap = batch;
+  }
+  rt_h2d(e->rt, e->d_rp_idx, indices, (size_t)batch * sizeof(int32_t));
+  int8_t* o_obs = outputs_on_device ? states : e->d_rp_obs;
+  float* o_pi = outputs_on_device ? pis : e->d_rp_pi;
+  float* o_z = outputs_on_device ? values : e->d_rp_z;
+  AZ_LAUNCH_THREADS(e->rt, k_replay_sample, (long long)batch * (d.obs_bytes + d.A), e->E, e->d_rp_idx, transform, o_obs, o_pi, o_z);
+  if (!outputs_on_device) {
+    rt_d2h(e->rt, states, o_obs, (size_t)batch * d.obs_bytes);
+    rt_d2h(e->rt, pis, o_pi, (size_t)batch * d.A * sizeof(float));
+    rt_d2h(e->rt, values, o_z, (size_t)batch * sizeof(float));
+  }
+  return rt_sync(e->rt);
 }

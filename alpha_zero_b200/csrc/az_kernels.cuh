@@ -269,3 +269,39 @@ AZ_GLOBAL k_scatter_eval(AzState E, const float* pri, const float* val, long lon
     if (a == 0) E.values[dst] = val[row];
   }
 }
+
+// Minibatch gather from the device replay with one dihedral transformation applied to the whole batch, exactly like
+// apply_random_transformation (utils/transformation.py:160): 0 none, 1 h_flip, 2 v_flip, 3/4/5 rotate 90/180/270
+// counter-clockwise (torchvision.rotate); the pass probability (Go) is not moved.
+AZ_DEV int az_src_cell(int n, int y, int x, int t) {
+  switch (t) {
+    case 1: return y * n + (n - 1 - x);
+    case 2: return (n - 1 - y) * n + x;
+    case 3: return x * n + (n - 1 - y);
+    case 4: return (n - 1 - y) * n + (n - 1 - x);
+    case 5: return (n - 1 - x) * n + y;
+    default: return y * n + x;
+  }
+}
+
+AZ_GLOBAL k_replay_sample(AzState E, const int32_t* idx, int transform, int8_t* out_obs, float* out_pi, float* out_z, long long n) {
+  // n = batch * (obs_bytes + A): one thread per output element
+  const AzDims& d = E.d;
+  const long long per = (long long)d.obs_bytes + d.A;
+  AZ_THREAD_LOOP(i, n) {
+    const long long b = i / per;
+    const int k = (int)(i - b * per);
+    const size_t src = (size_t)idx[b];
+    if (k < d.obs_bytes) {
+      const int plane = k / d.nc, c = k - plane * d.nc;
+      const int y = c / d.n, x = c - y * d.n;
+      out_obs[(size_t)b * d.obs_bytes + k] = E.rp_obs[src * d.obs_bytes + (size_t)plane * d.nc + az_src_cell(d.n, y, x, transform)];
+    } else {
+      const int a = k - d.obs_bytes;
+      int sa = a;
+      if (a < d.nc) { const int y = a / d.n, x = a - y * d.n; sa = az_src_cell(d.n, y, x, transform); }
+      out_pi[(size_t)b * d.A + a] = E.rp_pi[src * d.A + sa];
+      if (a == 0) out_z[b] = E.rp_z[src];
+    }
+  }
+}

@@ -132,6 +132,11 @@ struct AzState {
   int16_t* r_move;
   int32_t* games_ring;  // [ring_games][GR_INTS]
   unsigned long long* counters;  // see CT_*
+  // device-resident replay (learner input path): circular storage like replay.py:35-116
+  int8_t* rp_obs;       // [rp_cap][obs_bytes]
+  float* rp_pi;         // [rp_cap][A]
+  float* rp_z;          // [rp_cap]
+  int rp_cap;
 };
 
 enum { CT_SIMS = 0, CT_EVALS, CT_MOVES, CT_GAMES, CT_NODES, CT_DEPTH, CT_DESCENTS, CT_SAMPLES, CT_DROPPED, CT_ERRORS,

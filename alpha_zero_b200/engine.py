@@ -207,6 +207,43 @@ class Engine:
         n = ns.value
         return games, st[:n].reshape(n, self.planes, self.N, self.N), pis[:n], z[:n]
 
+    # ---- device-resident replay (learner input path) -----------------------------------------------
+    def replay_create(self, capacity):
+        self.b.check(self.b.dll.az_replay_create(self.h, int(capacity)))
+
+    def replay_ingest(self):
+        ng, ns = C.c_int32(), C.c_int32()
+        self.b.check(self.b.dll.az_replay_ingest(self.h, C.byref(ng), C.byref(ns)))
+        return int(ng.value), int(ns.value)
+
+    def replay_add(self, states, pis, values, n_games=1):
+        st = np.ascontiguousarray(states, dtype=np.int8).reshape(-1, self.obs_bytes)
+        pi = np.ascontiguousarray(pis, dtype=np.float32).reshape(st.shape[0], self.A)
+        z = np.ascontiguousarray(values, dtype=np.float32).reshape(st.shape[0])
+        self.b.check(self.b.dll.az_replay_add(self.h, as_ptr(st, C.c_int8), as_ptr(pi, C.c_float), as_ptr(z, C.c_float), st.shape[0], int(n_games)))
+
+    def replay_info(self):
+        a, g = C.c_int64(), C.c_int64()
+        sz, cap = C.c_int32(), C.c_int32()
+        self.b.check(self.b.dll.az_replay_info(self.h, C.byref(a), C.byref(g), C.byref(sz), C.byref(cap)))
+        return dict(num_samples_added=int(a.value), num_games_added=int(g.value), size=int(sz.value), capacity=int(cap.value))
+
+    def replay_sample(self, indices, transform=0, out=None):
+        """indices int32 [B] -> (states int8 [B,planes,N,N], pis f32 [B,A], values f32 [B]) on the host, or written into the
+        caller's CUDA tensors when out=(states_ptr, pis_ptr, values_ptr) device pointers are given."""
+        idx = i32(indices).ravel()
+        B = idx.size
+        if out is not None:
+            self.b.check(self.b.dll.az_replay_sample(self.h, as_ptr(idx, C.c_int32), B, int(transform), C.c_void_p(out[0]), C.c_void_p(out[1]),
+                                                     C.c_void_p(out[2]), 1))
+            return None
+        st = np.empty((B, self.obs_bytes), dtype=np.int8)
+        pi = np.empty((B, self.A), dtype=np.float32)
+        z = np.empty(B, dtype=np.float32)
+        self.b.check(self.b.dll.az_replay_sample(self.h, as_ptr(idx, C.c_int32), B, int(transform), as_ptr(st, C.c_int8), as_ptr(pi, C.c_float),
+                                                 as_ptr(z, C.c_float), 0))
+        return st.reshape(B, self.planes, self.N, self.N), pi, z
+
     def stream(self):
         p = C.c_void_p()
         self.b.check(self.b.dll.az_stream(self.h, C.byref(p)))

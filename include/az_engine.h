@@ -187,6 +187,21 @@ int az_stream(az_engine* e, void** cuda_stream);
 /* Time of the network kernels of the most recent az_selfplay_tick call, measured with CUDA events (ms). */
 int az_last_net_ms(az_engine* e, float* ms, int32_t* n_evals);
 
+/* ---- device-resident replay: the learner's input path -------------------------------
+ * UniformReplay (core/replay.py:35-116) with the storage in HBM: az_replay_ingest == add_game for every finished
+ * game, moved from the sample ring device-to-device (games taken here are no longer returned by az_drain_games);
+ * az_replay_add == add_game for host samples (other actors, --load_replay); az_replay_sample == get(indices) +
+ * the batch-wide dihedral transformation of utils/transformation.py:160 (0 none, 1 h_flip, 2 v_flip, 3/4/5 rotate
+ * 90/180/270) fused into the gather.  Indices come from the caller, so `random_state.randint(0, size, batch)`
+ * (core/replay.py:75) on the host reproduces the reference's minibatches.  Outputs go to host buffers or, with
+ * outputs_on_device != 0, to caller-owned device pointers (e.g. torch CUDA tensors of the learner). */
+int az_replay_create(az_engine* e, int32_t capacity);
+int az_replay_ingest(az_engine* e, int32_t* n_games, int32_t* n_samples);
+int az_replay_add(az_engine* e, const int8_t* states, const float* pis, const float* values, int32_t n, int32_t n_games);
+int az_replay_info(az_engine* e, int64_t* num_samples_added, int64_t* num_games_added, int32_t* size, int32_t* capacity);
+int az_replay_sample(az_engine* e, const int32_t* indices, int32_t batch, int32_t transform, int8_t* states, float* pis,
+                     float* values, int32_t outputs_on_device);
+
 #ifdef __cplusplus
 }
 #endif

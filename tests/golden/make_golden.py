@@ -619,6 +619,36 @@ def part_pro_go9():
     print('pro_go9:', len(files), 'games,', len(all_moves), 'moves')
 
 
+
+def part_transform():
+    """utils/transformation.py:160 (learner-side augmentation): every supported transformation applied by
+    the reference itself to random (state, pi) batches, with and without the pass column."""
+    import numpy as np
+    import torch
+    from alpha_zero.utils import transformation as tr
+
+    out = {}
+    gen = torch.Generator().manual_seed(5)
+    for tag, n, has_pass in (('go9', 9, True), ('gomoku13', 13, False), ('go19', 19, True)):
+        a = n * n + (1 if has_pass else 0)
+        st = (torch.rand((6, 17, n, n), generator=gen) < 0.3).to(torch.float32)
+        pi = torch.rand((6, a), generator=gen)
+        pi = pi / pi.sum(dim=1, keepdim=True)
+        v = torch.rand((6,), generator=gen) * 2 - 1
+        out[tag + '/state'] = st.numpy().astype(np.int8)
+        out[tag + '/pi'] = pi.numpy()
+        out[tag + '/value'] = v.numpy()
+        for name in tr.TRANSFORMATIONS:
+            s2, p2, v2 = tr.SUPPORTED_TRANSFORMATIONS[name](st, pi, v)
+            out[f'{tag}/{name}/state'] = s2.numpy().astype(np.int8)
+            out[f'{tag}/{name}/pi'] = p2.numpy()
+            assert torch.equal(v2, v)
+    out['names'] = np.array(tr.TRANSFORMATIONS)
+    out['versions'] = versions()
+    np.savez_compressed(os.path.join(HERE, 'transform.npz'), **out)
+    print('transform: ok', tr.TRANSFORMATIONS)
+
+
 PARTS = {
     'go9_selfplay': (part_go9_selfplay, 9),
     'gomoku13_selfplay': (part_gomoku13_selfplay, 9),
@@ -634,6 +664,7 @@ PARTS = {
     'random_go9': (part_random_go9_full, 9),
     'random_gomoku15': (part_random_gomoku15, 9),
     'pro_go9': (part_pro_go9, 9),
+    'transform': (part_transform, 9),
 }
 
 
