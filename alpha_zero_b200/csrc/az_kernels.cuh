@@ -89,6 +89,8 @@ AZ_GLOBAL k_selfplay_begin(AzState E, int nwarps) {
   AZ_WARP_INDEX(nwarps) {
     Sim S;
     AZ_SCRATCH(E.d, S);
+    W_LANE0 E.tree_i[(size_t)az_g * TREE_INTS + TI_SLOT_GAMES] = 0;
+    w_sync();
     game_new(E, az_g, S);
     W_LANE0 E.tree_i[(size_t)az_g * TREE_INTS + TI_ACTIVE] = 1;
   }

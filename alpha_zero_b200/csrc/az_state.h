@@ -47,6 +47,7 @@ enum {
   TI_MARKED,        // marked_resign_player (0 none)
   TI_GAME_UID,
   TI_ACTIVE,        // slot takes part in the current split-phase search batch
+  TI_SLOT_GAMES,    // games started in this slot since az_selfplay_begin (makes the RNG streams independent of warp scheduling)
   TREE_INTS = 16
 };
 

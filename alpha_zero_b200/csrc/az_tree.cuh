@@ -525,7 +525,10 @@ AZ_DEV void game_new(const AzState& E, int g, Sim& S) {
   int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
   env_reset(E, g, S);
   W_LANE0 {
-    const unsigned long long uid = atomic_add_u64(&E.counters[CT_COUNT - 1], 1ull);
+    // game id = (games started in this slot) * G + slot: unique, and a function of (seed, slot, history) only, so a run is
+    // reproducible no matter in which order the warps get here
+    const unsigned long long uid = (unsigned long long)ti[TI_SLOT_GAMES] * (unsigned long long)E.d.G + (unsigned long long)g;
+    ti[TI_SLOT_GAMES] += 1;
     ti[TI_GAME_UID] = (int)uid;
     ti[TI_GAME_PLY] = 0;
     ti[TI_MARKED] = 0;
