@@ -129,10 +129,6 @@ AZ_GLOBAL k_env_step(AzState E, const int32_t* slots, const int32_t* actions, in
       const StepOut o = env_step(E, g, S, a);
       rx2 = o.reward_x2;
       done = o.done;
-      W_LANE0 {  // the position moved: any tree of this slot that was not re-rooted is stale
-        int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
-        (void)ti;
-      }
     }
     W_LANE0 { out[az_g * 3] = err; out[az_g * 3 + 1] = rx2; out[az_g * 3 + 2] = done; }
   }

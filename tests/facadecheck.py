@@ -166,3 +166,49 @@ def pipeline_traces(game):
         np.testing.assert_array_equal(np.stack([t.state for t in seq]), z[f'{name}/states'])
         np.testing.assert_allclose(np.stack([np.asarray(t.pi_prob, dtype=np.float64) for t in seq]), z[f'{name}/pis'], rtol=0, atol=1e-12)
         np.testing.assert_array_equal(np.array([t.value for t in seq], dtype=np.float32), z[f'{name}/values'])
+
+
+def error_paths():
+    """Argument / state errors surface as the reference's exception types (mcts_v2.py:356-361) or as EngineError."""
+    import pytest
+
+    from alpha_zero_b200._lib import EngineError
+    from alpha_zero_b200.engine import Engine
+    from alpha_zero_b200.envs import _pool
+    from alpha_zero_b200.mcts import Node, parallel_uct_search, uct_search
+
+    ev = make_fake_eval(82)
+    env = make_env('go9')
+    env.reset()
+    with pytest.raises(ValueError, match='num_simulations'):
+        uct_search(env, ev, None, 19652.0, 1.25, 0)
+    with pytest.raises(ValueError, match='BoardGameEnv'):
+        uct_search(object(), ev, None, 19652.0, 1.25, 8)
+    with pytest.raises(ValueError, match='root_node'):
+        parallel_uct_search(env, ev, Node(to_play=1, num_actions=82), 19652.0, 1.25, 8, 4)  # a handle that is not this env's tree
+    mv, pi, rq, cq, nxt = parallel_uct_search(env, ev, None, 19652.0, 1.25, 16, 4, False, True, True)
+    env.step(mv)
+    other = make_env('go9')
+    other.reset()
+    with pytest.raises(ValueError, match='root_node'):
+        uct_search(other, ev, nxt, 19652.0, 1.25, 8)  # subtree of another env
+    env.step(env.pass_move)
+    env.step(env.pass_move)
+    assert env.is_game_over()
+    with pytest.raises(RuntimeError, match='Game is over'):
+        uct_search(env, ev, None, 19652.0, 1.25, 8)
+    # engine-level capacity and argument checks
+    eng = Engine('go', 9, num_games=2, max_simulations=32, max_parallel=4, binding=_pool._TEST_BINDING)
+    with pytest.raises(EngineError, match='node pool'):
+        eng.search_begin([0], [0], 19652.0, 1.25, 4000, 4)
+    with pytest.raises(EngineError, match='max_parallel'):
+        eng.search_begin([0], [0], 19652.0, 1.25, 16, 64)
+    with pytest.raises(ValueError, match='slot'):
+        eng.env_reset([5])
+    with pytest.raises(ValueError, match='ascending'):
+        eng.search_begin([1, 0], [0, 0], 19652.0, 1.25, 16, 4)
+    with pytest.raises(EngineError, match='no search in progress|not finished'):
+        eng.search_result(1)
+    with pytest.raises(Exception):
+        Engine('go', 25, num_games=1, binding=_pool._TEST_BINDING)  # board size out of range
+    eng.close()

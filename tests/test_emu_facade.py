@@ -30,3 +30,7 @@ def test_mcts_api_traces(game):
 @pytest.mark.parametrize('game', ['go9', 'gomoku13'])
 def test_pipeline_traces(game):
     facadecheck.pipeline_traces(game)
+
+
+def test_error_paths():
+    facadecheck.error_paths()

@@ -25,6 +25,10 @@ def test_env_contract():
     facadecheck.env_contract()
 
 
+def test_error_paths():
+    facadecheck.error_paths()
+
+
 @pytest.mark.parametrize('game', ['go9', 'gomoku13'])
 def test_mcts_api_traces(game):
     assert facadecheck.mcts_api_traces(game) > 40
