@@ -45,6 +45,14 @@ def _device_index(device):
     return int(idx or 0)
 
 
+def _env_kind(env):
+    """'go' | 'gomoku' for our façades and for the reference's own env objects (GoEnv has a pass move, GomokuEnv has not)."""
+    kind = getattr(env, 'game', None)
+    if kind in ('go', 'gomoku'):
+        return kind
+    return 'go' if getattr(env, 'has_pass_move', False) else 'gomoku'
+
+
 class _NetOnEngine:
     """The nn.Module's parameters copied into an engine-owned network; refreshed when the module changes
     (the actor loop hot-swaps checkpoints with load_state_dict, pipeline.py:232-239)."""
@@ -85,7 +93,7 @@ def create_mcts_player(network, device, num_simulations, num_parallel, root_nois
 
     def act(env, root_node, c_puct_base, c_puct_init, warm_up=False):
         if 'ev' not in holder:
-            holder['ev'] = EngineEvaluator(_NetOnEngine(network, device, env.game, env.board_size))
+            holder['ev'] = EngineEvaluator(_NetOnEngine(network, device, _env_kind(env), env.board_size))
         if num_parallel > 1:
             return parallel_uct_search(env=env, eval_func=eval_position, root_node=root_node, c_puct_base=c_puct_base, c_puct_init=c_puct_init,
                                        num_simulations=num_simulations, num_parallel=num_parallel, root_noise=root_noise, warm_up=warm_up,
@@ -153,7 +161,7 @@ def games_to_queue_items(engine, env, games, states, pis, zs, moves, resign_thre
     for g in games:
         s0, ln = g['first_sample'], g['game_length']
         seq = [Transition(state=states[s0 + i].copy(), pi_prob=pis[s0 + i].astype(pi_dtype), value=float(zs[s0 + i])) for i in range(ln)]
-        stats = {'game_length': ln, 'game_result': _result_string(g, env.game)}
+        stats = {'game_length': ln, 'game_result': _result_string(g, _env_kind(env))}
         if env.has_pass_move:
             stats['num_passes'] = g['num_passes']
         if env.has_resign_move:
@@ -194,7 +202,8 @@ def run_selfplay_actor_loop(seed, rank, network, device, data_queue, env, num_si
     blocks, filters, fc = _net_geometry(network)
     games = int(os.environ.get('AZ_ACTOR_GAMES', '1024'))
     par = max(1, int(num_parallel))
-    engine = Engine(env.game, env.board_size, num_games=games, max_simulations=num_simulations, max_parallel=par,
+    kind = _env_kind(env)  # `env` may be our façade or the reference's own GoEnv / GomokuEnv: only its settings are read
+    engine = Engine(kind, env.board_size, num_games=games, max_simulations=num_simulations, max_parallel=par,
                     komi=getattr(env, 'komi', 0.0), max_steps=getattr(env, 'max_steps', 0), num_to_win=getattr(env, 'num_to_win', 5),
                     num_stack=env.num_stack, net=(blocks, filters, fc), precision=os.environ.get('AZ_NET_PRECISION', 'bf16'),
                     device=_device_index(device), seed=int(seed + rank))

@@ -61,3 +61,22 @@ def test_items_feed_reference_replay_and_losses(game):
     policy_loss, value_loss = compute_losses(net, torch.device('cpu'), batch, False)
     assert torch.isfinite(policy_loss) and torch.isfinite(value_loss)
     (policy_loss + value_loss).backward()
+
+
+def test_actor_accepts_reference_env_objects():
+    """run_selfplay_actor_loop only reads settings from `env`: the reference's GoEnv / GomokuEnv instances map to the right engine."""
+    for p in (os.path.join(os.path.dirname(os.path.abspath(__file__)), 'shims'), REF):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.setdefault('BOARD_SIZE', '9')
+    from alpha_zero.envs.go import GoEnv as RefGo
+    from alpha_zero.envs.gomoku import GomokuEnv as RefGomoku
+
+    from alpha_zero_b200.pipeline import _env_kind, games_to_queue_items
+
+    go, gm = RefGo(komi=5.5, num_stack=8, max_steps=60), RefGomoku(board_size=13, num_to_win=5, num_stack=8)
+    assert _env_kind(go) == 'go' and _env_kind(gm) == 'gomoku'
+    assert (go.board_size, go.komi, go.max_steps, go.num_stack) == (9, 5.5, 60, 8) and gm.num_to_win == 5
+    games, states, pis, zs, moves = _fake_finished_games(2, 82, 9, True)
+    (seq, stats, hist), _ = games_to_queue_items(None, go, games, states, pis, zs, moves, resign_threshold=-0.9)
+    assert stats['game_result'] in ('B+R', 'W+R', 'B+3.5') and stats['marked_resign_player'] is None and 'num_passes' in stats
