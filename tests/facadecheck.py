@@ -212,3 +212,37 @@ def error_paths():
     with pytest.raises(Exception):
         Engine('go', 25, num_games=1, binding=_pool._TEST_BINDING)  # board size out of range
     eng.close()
+
+
+def batched_matches(game):
+    """play_matches (evaluation matches, many games in lock step) vs the oracle playing the same match alone: with one game and
+    a seeded numpy RNG the move list is identical (no reuse, no noise, T=0.1 sampling); with several games every game is a legal,
+    finished game whose result string matches an oracle replay."""
+    from alpha_zero_b200.envs import _pool
+    from alpha_zero_b200.matches import play_matches
+    from oracle.boards import GoBoard, GomokuBoard
+    from oracle.search import search
+
+    kind, n, A = ('go', 9, 82) if game == 'go9' else ('gomoku', 13, 169)
+    ev_b, ev_w = make_fake_eval(A, sharpness=2.0), make_fake_eval(A, sharpness=3.0)
+    kw = dict(num_simulations=24, num_parallel=4, max_steps=30 if kind == 'go' else 0, binding=_pool._TEST_BINDING)
+    np.random.seed(21)
+    one = play_matches(1, kind, n, ev_b, ev_w, **kw)[0]
+    np.random.seed(21)
+    env = GoBoard(9, 7.5, 8, 30) if kind == 'go' else GomokuBoard(13, 5, 8)
+    mvs, side = [], 0
+    while not env.is_game_over():
+        mv, *_ = search(env, (ev_b, ev_w)[side], None, 19652.0, 1.25, 24, 4, False, False, False)
+        env.step(mv)
+        mvs.append(mv)
+        side ^= 1
+    assert one['moves'] == mvs and one['game_result'] == env.get_result_string() and one['game_length'] == env.steps
+    np.random.seed(22)
+    many = play_matches(6, kind, n, ev_b, ev_w, **kw)
+    assert len({tuple(g['moves']) for g in many}) > 1  # sampled games differ
+    for g in many:
+        env.reset()
+        for mv in g['moves']:
+            assert env.legal_actions[mv] == 1
+            env.step(mv)
+        assert env.is_game_over() and env.get_result_string() == g['game_result'] and env.steps == g['game_length']

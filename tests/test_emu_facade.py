@@ -34,3 +34,8 @@ def test_pipeline_traces(game):
 
 def test_error_paths():
     facadecheck.error_paths()
+
+
+@pytest.mark.parametrize('game', ['go9', 'gomoku13'])
+def test_batched_matches(game):
+    facadecheck.batched_matches(game)
