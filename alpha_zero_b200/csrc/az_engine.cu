@@ -297,6 +297,39 @@ extern "C" int az_env_step(az_engine* e, const int32_t* slots, const int32_t* ac
   return AZ_OK;
 }
 
+extern "C" int az_env_replay(az_engine* e, const int32_t* slots, int32_t n, const int16_t* moves, const int32_t* offsets, int8_t* states,
+                             int32_t* n_played, int32_t* status) {
+  int rc = upload_slots(e, slots, n);
+  if (rc) return rc;
+  if (!moves || !offsets || !n_played || !status) return az_fail(AZ_ERR_BAD_ARG, "null argument");
+  if (offsets[0] != 0) return az_fail(AZ_ERR_BAD_ARG, "offsets[0] must be 0");
+  std::vector<char> seen((size_t)e->E.d.G, 0);
+  for (int i = 0; i < n; ++i) {
+    if (offsets[i + 1] < offsets[i]) return az_fail(AZ_ERR_BAD_ARG, "offsets must be non-decreasing");
+    if (seen[slots[i]]++) return az_fail(AZ_ERR_BAD_ARG, "duplicate slot in replay list");
+  }
+  const size_t total = (size_t)offsets[n], ob = (size_t)e->E.d.obs_bytes;
+  int16_t* d_moves = (int16_t*)rt_alloc((total + 1) * sizeof(int16_t));
+  int32_t* d_off = (int32_t*)rt_alloc((size_t)(n + 1) * sizeof(int32_t));
+  int32_t* d_res = (int32_t*)rt_alloc((size_t)n * 2 * sizeof(int32_t));
+  int8_t* d_states = states && total ? (int8_t*)rt_alloc(total * ob) : nullptr;
+  if (!d_moves || !d_off || !d_res || (states && total && !d_states)) {
+    rt_free(d_moves); rt_free(d_off); rt_free(d_res); rt_free(d_states);
+    return az_fail(AZ_ERR_CUDA, "az_env_replay: out of device memory for " + std::to_string(total) + " positions");
+  }
+  if (total) rt_h2d(e->rt, d_moves, moves, total * sizeof(int16_t));
+  rt_h2d(e->rt, d_off, offsets, (size_t)(n + 1) * sizeof(int32_t));
+  AZ_LAUNCH_WARPS(e->rt, k_env_replay, n, e->E.d, e->E, e->d_slots, d_moves, d_off, d_states, d_res);
+  std::vector<int32_t> res((size_t)n * 2);
+  rt_d2h(e->rt, res.data(), d_res, res.size() * sizeof(int32_t));
+  if (d_states) rt_d2h(e->rt, states, d_states, total * ob);  // rows of games that stopped early stay zero past n_played
+  rc = rt_sync(e->rt);
+  rt_free(d_moves); rt_free(d_off); rt_free(d_res); rt_free(d_states);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i) { n_played[i] = res[i * 2]; status[i] = res[i * 2 + 1]; }
+  return AZ_OK;
+}
+
 extern "C" int az_env_observation(az_engine* e, int32_t slot, int8_t* out) {
   int rc = check_slot(e, slot);
   if (rc) return rc;

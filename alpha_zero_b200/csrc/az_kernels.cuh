@@ -134,6 +134,41 @@ AZ_GLOBAL k_env_step(AzState E, const int32_t* slots, const int32_t* actions, in
   }
 }
 
+// Replay of recorded games (core/eval_dataset.py:166-215, the loop of replay_sgf): one warp resets its slot and plays its
+// move list, writing the observation BEFORE every move (the dataset's `state`) to states[(offsets[i] + t)].  Stops at the
+// first move step() would reject (same validation order as k_env_step); out = {moves played, error code} per game.
+AZ_GLOBAL k_env_replay(AzState E, const int32_t* slots, const int16_t* moves, const int32_t* offsets, int8_t* states, int32_t* out, int nwarps) {
+  AZ_WARP_INDEX(nwarps) {
+    Sim S;
+    AZ_SCRATCH(E.d, S);
+    const int g = slots[az_g];
+    env_reset(E, g, S);
+    W_LANE0 {
+      int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
+      ti[TI_STATE] = ST_IDLE;
+      ti[TI_NODES] = 0;
+      ti[TI_ACTIVE] = 0;
+    }
+    w_sync();
+    const int first = offsets[az_g], n = offsets[az_g + 1] - first;
+    const int32_t* ei = E.env_i + (size_t)g * ENV_INTS;
+    int t = 0, err = 0;
+    for (; t < n; ++t) {
+      const int a = moves[first + t];
+      if (ei[EI_DONE]) err = -4;
+      else if (a < 0 || a >= E.d.A) err = -2;
+      else if (E.root_legal[(size_t)g * E.d.Ap + a] != 1) err = -3;
+      if (err) break;
+      if (states) {
+        sim_load(E, g, S);
+        sim_write_obs(E.d, S, states + (size_t)(first + t) * E.d.obs_bytes);
+      }
+      env_step(E, g, S, a);
+    }
+    W_LANE0 { out[az_g * 2] = t; out[az_g * 2 + 1] = err; }
+  }
+}
+
 AZ_GLOBAL k_env_obs(AzState E, int slot, int8_t* out, int nwarps) {
   AZ_WARP_INDEX(nwarps) {
     Sim S;

@@ -123,6 +123,28 @@ class Engine:
         buf = np.frombuffer(blob, dtype=np.uint8).copy()
         self.b.check(self.b.dll.az_env_import(self.h, int(slot), as_ptr(buf, C.c_uint8)))
 
+    def env_replay(self, slots, games, want_states=True):
+        """Replay `games` (lists of flat actions) on `slots`, one warp per game in one kernel (core/eval_dataset.py:166-215).
+        Returns (states [total, planes, N, N] int8 or None, offsets, n_played, status); states[offsets[i] + t] is the observation
+        before move t of game i; a game stops at its first rejected move (status < 0)."""
+        s = i32(slots).ravel()
+        n = len(s)
+        if len(games) != n:
+            raise ValueError('one move list per slot')
+        offsets = np.zeros(n + 1, dtype=np.int32)
+        offsets[1:] = np.cumsum([len(g) for g in games])
+        flat = np.asarray([a for g in games for a in g], dtype=np.int64)
+        if flat.size and (flat.min() < -32768 or flat.max() > 32767):
+            raise ValueError('action out of int16 range')
+        moves = np.ascontiguousarray(flat, dtype=np.int16) if flat.size else np.zeros(1, dtype=np.int16)
+        states = np.zeros((int(offsets[-1]), self.planes, self.N, self.N), dtype=np.int8) if want_states else None
+        played = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        self.b.check(self.b.dll.az_env_replay(self.h, as_ptr(s, C.c_int32), n, as_ptr(moves, C.c_int16), as_ptr(offsets, C.c_int32),
+                                              as_ptr(states, C.c_int8) if want_states and states.size else None,
+                                              as_ptr(played, C.c_int32), as_ptr(status, C.c_int32)))
+        return states, offsets, played, status
+
     # ---- search (split phase) ---------------------------------------------------------------------
     def search_begin(self, slots, reuse, c_puct_base, c_puct_init, num_simulations, num_parallel, root_noise=False,
                      warm_up=False, deterministic=False, noise=None):

@@ -141,6 +141,13 @@ int az_env_copy(az_engine* e, int32_t src_slot, int32_t dst_slot);              
 int az_env_state_bytes(az_engine* e);
 int az_env_export(az_engine* e, int32_t slot, uint8_t* out);                    /* pickling */
 int az_env_import(az_engine* e, int32_t slot, const uint8_t* in);
+/* Replay of recorded games = the loop of replay_sgf (core/eval_dataset.py:166-215) for n games at once: slot i is reset and
+ * plays moves[offsets[i] .. offsets[i+1]) (flat actions); states (host, offsets[n]*az_obs_bytes, may be NULL) receives the
+ * observation BEFORE each move at row offsets[i]+t.  A game stops at the first move step() would reject: n_played[i] moves
+ * were played, status[i] = 0 or AZ_ERR_GAME_OVER / AZ_ERR_INVALID_ACTION / AZ_ERR_ILLEGAL_ACTION.  The slots keep the final
+ * positions (az_env_scalars / az_env_score / az_env_board). */
+int az_env_replay(az_engine* e, const int32_t* slots, int32_t n, const int16_t* moves, const int32_t* offsets, int8_t* states,
+                  int32_t* n_played, int32_t* status);
 
 /* ---- search, split phase: the evaluator lives outside (a Python eval_func, a fake, torch) --------
  * az_search_begin : start uct_search/parallel_uct_search on `slots`; reuse[i]!=0 keeps the slot's

@@ -19,6 +19,7 @@ Files (all small, compressed):
   mcts_<game>.npz       uct_search / parallel_uct_search traces under the deterministic fake evaluator.
   net.npz               AlphaZeroNet forward (small random nets, BN statistics randomised) inputs/outputs.
   pipeline_<game>.npz   play_and_record_one_game end-to-end traces (seeded numpy RNG, small CPU net).
+  eval_dataset_go9.npz  replay_sgf (core/eval_dataset.py:80) on 410 recorded games: kept / dropped, per-game digests, MISMATCH_GAMES.
 """
 import argparse
 import hashlib
@@ -620,6 +621,42 @@ def part_pro_go9():
 
 
 
+def part_eval_dataset_go9():
+    """core/eval_dataset.py:80 replay_sgf run by the reference itself (through the `sgf` stand-in of tests/shims) on a mixed
+    list of files: human 9x9 games, the CrazyStone matches (scored results: MISMATCH_GAMES statistics) and self-play records
+    (same two player names: duplicate and games-per-player filters).  The SGF texts travel inside the fixture."""
+    import logging
+    import numpy as np
+    from alpha_zero.core import eval_dataset as ed
+
+    def pick(sub, k):
+        d = os.path.join(REF, 'games', sub)
+        return [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith('.sgf')][:k]
+
+    files = pick('pro_games/go/9x9', 260) + pick('9x9_matches/crazystone_vs_az', 20) + pick('selfplay_games/go/9x9', 130)
+    logger = logging.getLogger('golden')
+    logger.setLevel(logging.CRITICAL)
+    texts, valid, counts, digests = [], [], [], []
+    for path in files:
+        texts.append(open(path).read())
+        h = ed.replay_sgf(path, 8, logger)
+        valid.append(h is not None)
+        sha = hashlib.sha1()
+        for obs, pi, v in (h or []):
+            assert obs.dtype == np.int8 and obs.shape == (17, 9, 9)
+            sha.update(obs.tobytes())
+            sha.update(np.int32(int(np.argmax(pi))).tobytes())
+            sha.update(np.float32(v).tobytes())
+        counts.append(len(h) if h is not None else -1)
+        digests.append(sha.hexdigest())
+    mm = ed.MISMATCH_GAMES
+    out = dict(names=np.array([os.path.relpath(f, os.path.join(REF, 'games')) for f in files]), texts=np.array(texts), valid=np.array(valid),
+               counts=np.array(counts, dtype=np.int32), digest=np.array(digests), mismatch_keys=np.array(list(mm.keys())),
+               mismatch_values=np.array(list(mm.values()), dtype=np.int32), versions=versions())
+    np.savez_compressed(os.path.join(HERE, 'eval_dataset_go9.npz'), **out)
+    print('eval_dataset_go9:', len(files), 'files,', int(np.sum(valid)), 'valid,', int(np.sum(np.maximum(counts, 0))), 'positions,', dict(mm))
+
+
 def part_transform():
     """utils/transformation.py:160 (learner-side augmentation): every supported transformation applied by
     the reference itself to random (state, pi) batches, with and without the pass column."""
@@ -665,6 +702,7 @@ PARTS = {
     'random_gomoku15': (part_random_gomoku15, 9),
     'pro_go9': (part_pro_go9, 9),
     'transform': (part_transform, 9),
+    'eval_dataset_go9': (part_eval_dataset_go9, 9),
 }
 
 
