@@ -32,6 +32,7 @@ struct AzNetTc {
   CUtensorMap hmap_in[2], hmap_x[2], hmap_mid[2];  // halo kernel: [0] 256-row box, [1] tail box (AR-256 rows)
   int mode = 0;            // AZ_TC_MODE: 0 = one TMA box per tap, 1/2 = halo tile + row-shifted descriptors (base-offset variants)
   int halo = 0, AR = 0;
+  int res_l2 = 0;
   size_t halo_smem = 0;
   std::vector<CUtensorMap> map_w;
   std::vector<CUtensorMap> map_w_half;  // pair kernel: box of cout/2 weight rows
@@ -285,6 +286,7 @@ struct HaloLayer {
   int Wr, Hc, RP, guard;
   int halo, AR;   // halo rows on each side; rows of the staged tile (multiple of 8)
   int bo_mode;    // experiment switch: 1 puts (start >> 7) & 7 into the descriptor's base-offset field (wrong on B200)
+  int res_l2;     // 1: the producer asks TMA to pull the residual rows of the NEXT tile into L2 (AZ_TC_RESPF)
 };
 
 
@@ -300,6 +302,10 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m
                    smem_u32(dst)),
                "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(x), "r"(y)
                : "memory");
+}
+// L2 prefetch of a tensor-map box (no shared-memory destination, no barrier): a hint, results never depend on it
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int x, int y) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
 }
 __device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -330,7 +336,7 @@ __device__ __forceinline__ bool elect_one() {
 template <bool PAIR>
 __global__ void __launch_bounds__(H_THREADS, 1)
 k_conv_tc_halo(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b,
-               const float* __restrict__ bias, const __nv_bfloat16* res, __nv_bfloat16* out, const int32_t* __restrict__ n_rows, HaloLayer L) {
+               const __grid_constant__ CUtensorMap map_r, const float* __restrict__ bias, const __nv_bfloat16* res, __nv_bfloat16* out, const int32_t* __restrict__ n_rows, HaloLayer L) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int kc = L.cin / TC_BK;
@@ -418,8 +424,15 @@ k_conv_tc_halo(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           }
         }
       };
+      // residual rows (256 x cout of the block input) of a tile, pulled into L2 one tile before the epilogue's register
+      // prefetch asks for them: the epilogue's dependent loads then see L2 latency instead of HBM latency
+      auto res_to_l2 = [&](int u) {
+        const int tt = PAIR ? 2 * u + (int)crank : u;
+        for (int c = 0; c < L.cout; c += TC_BK) tma_prefetch_l2_2d(&map_r, c, L.guard + tt * 256);
+      };
       if (unit0 < num_units) load_a(0, unit0);
       for (int u = unit0; u < num_units; u += ustep, ++it) {
+        if (L.res_l2 && u + ustep < num_units) res_to_l2(u + ustep);
         for (int tap = 0; tap < 9; ++tap) {
           if (tap == 3 && u + ustep < num_units) load_a(it + 1, u + ustep);
           for (int kk = 0; kk < kc; ++kk) {
@@ -668,6 +681,8 @@ int aznet_tc_create(AzNet* n, AzRt& rt, std::string& err) {
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&tc->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  const char* rp = getenv("AZ_TC_RESPF");
+  tc->res_l2 = rp ? atoi(rp) : 0;
   const char* md = getenv("AZ_TC_MODE");
   tc->mode = md ? atoi(md) : 4;  // 4 = halo tile + 2-CTA pairs (default), 2 = halo tile single CTA, 0 = one TMA box per tap
   if (n->C > 128) tc->mode = 0;  // the halo tile of a 256-channel layer does not fit next to the weight ring
@@ -765,7 +780,7 @@ int aznet_tc_forward(AzNet* n, AzRt& rt, const int8_t* obs_base, const int32_t* 
     const bool pair = tc->mode == 4;
     auto launch = [&](const CUtensorMap* ma, int wi, const float* bias, const __nv_bfloat16* resp, __nv_bfloat16* outp) {
       if (!pair) {
-        k_conv_tc_halo<false><<<hgrid, H_THREADS, tc->halo_smem, rt.stream>>>(ma[0], ma[1], tc->map_w[wi], bias, resp, outp, n_rows_dev, H);
+        k_conv_tc_halo<false><<<hgrid, H_THREADS, tc->halo_smem, rt.stream>>>(ma[0], ma[1], tc->map_w[wi], tc->hmap_x[0], bias, resp, outp, n_rows_dev, H);
       } else {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(hgrid & ~1));
@@ -777,17 +792,17 @@ int aznet_tc_forward(AzNet* n, AzRt& rt, const int8_t* obs_base, const int32_t* 
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, k_conv_tc_halo<true>, ma[0], ma[1], tc->map_w_half[wi], bias, resp, outp, n_rows_dev, H);
+        cudaLaunchKernelEx(&cfg, k_conv_tc_halo<true>, ma[0], ma[1], tc->map_w_half[wi], tc->hmap_x[0], bias, resp, outp, n_rows_dev, H);
       }
       rt.launches++;
     };
-    H.cin = 64; H.cout = n->C; H.relu = 1; H.has_res = 0;
+    H.cin = 64; H.cout = n->C; H.relu = 1; H.has_res = 0; H.res_l2 = 0;
     launch(tc->hmap_in, 0, n->conv_b[0], nullptr, X);
     H.cin = n->C;
     for (int b = 0; b < n->blocks; ++b) {
-      H.has_res = 0;
+      H.has_res = 0; H.res_l2 = 0;
       launch(tc->hmap_x, 1 + 2 * b, n->conv_b[1 + 2 * b], nullptr, MID);
-      H.has_res = 1;
+      H.has_res = 1; H.res_l2 = tc->res_l2;  // the residual is always act_x (hmap_x)
       launch(tc->hmap_mid, 2 + 2 * b, n->conv_b[2 + 2 * b], X, X);
     }
     launch_heads<__nv_bfloat16>(rt.stream, X, row_list, n_rows_dev, n->hp, g, n->C, n->A, n->fc, priors_base, values_base, pri_stride, max_rows);
