@@ -603,12 +603,30 @@ extern "C" int az_selfplay_begin(az_engine* e, const az_selfplay_params* p) {
 extern "C" int az_selfplay_update(az_engine* e, const az_selfplay_params* p) {
   if (!e || !p) return az_fail(AZ_ERR_BAD_ARG, "null argument");
   if (!e->selfplay) return az_fail(AZ_ERR_STATE, "az_selfplay_update: call az_selfplay_begin first");
+  if (p->search.c_puct_base > 0.0) {  // new search parameters from the next leaf batch on; searches in flight run to the new bound
+    int rc = rt_sync(e->rt);          // the tables / AzSearchCfg travel with the next launches; nothing of the old ones may be in flight
+    if (!rc) rc = set_search_cfg(e, &p->search);
+    if (rc) return rc;
+  }
   AzSearchCfg& s = e->E.s;  // games in flight keep running; only the per-move / per-new-game policy knobs change
   s.warm_up_steps = p->warm_up_steps;
   s.check_resign_after = p->check_resign_after_steps;
   s.resign_threshold = p->resign_threshold;
   s.disable_resign_ratio = p->disable_resign_ratio;
   return AZ_OK;
+}
+
+extern "C" int az_selfplay_restart(az_engine* e, const int32_t* slots, int32_t n) {
+  if (!e) return az_fail(AZ_ERR_BAD_ARG, "null engine");
+  if (!e->selfplay) return az_fail(AZ_ERR_STATE, "az_selfplay_restart: call az_selfplay_begin first");
+  if (n == 0) return AZ_OK;
+  int rc = upload_slots(e, slots, n);
+  if (rc) return rc;
+  std::vector<char> seen((size_t)e->E.d.G, 0);
+  for (int i = 0; i < n; ++i)
+    if (seen[slots[i]]++) return az_fail(AZ_ERR_BAD_ARG, "az_selfplay_restart: duplicate slot");
+  AZ_LAUNCH_WARPS(e->rt, k_selfplay_restart, n, e->E.d, e->E, e->d_slots);
+  return rt_sync(e->rt);
 }
 
 extern "C" int az_selfplay_tick(az_engine* e, int32_t n_ticks) {

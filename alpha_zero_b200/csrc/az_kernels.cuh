@@ -96,6 +96,15 @@ AZ_GLOBAL k_selfplay_begin(AzState E, int nwarps) {
   }
 }
 
+// az_selfplay_restart: the running game of slots[i] is abandoned (nothing emitted) and a new one starts in its place
+AZ_GLOBAL k_selfplay_restart(AzState E, const int32_t* slots, int nwarps) {
+  AZ_WARP_INDEX(nwarps) {
+    Sim S;
+    AZ_SCRATCH(E.d, S);
+    game_new(E, slots[az_g], S);
+  }
+}
+
 AZ_GLOBAL k_env_reset(AzState E, const int32_t* slots, int nwarps) {
   AZ_WARP_INDEX(nwarps) {
     Sim S;

@@ -199,9 +199,21 @@ class Engine:
                               int(warm_up_steps), int(check_resign_after_steps), float(resign_threshold), float(disable_resign_ratio))
         self.b.check(self.b.dll.az_selfplay_begin(self.h, C.byref(sp)))
 
-    def selfplay_update(self, warm_up_steps, check_resign_after_steps, resign_threshold, disable_resign_ratio):
-        sp = AzSelfplayParams(AzSearchParams(0.0, 0.0, 1, 1, 0, 0), int(warm_up_steps), int(check_resign_after_steps), float(resign_threshold), float(disable_resign_ratio))
+    def selfplay_update(self, warm_up_steps, check_resign_after_steps, resign_threshold, disable_resign_ratio, search=None):
+        """Policy knobs of the running loop; `search` = dict(num_simulations, num_parallel[, c_puct_base, c_puct_init, root_noise,
+        deterministic]) also replaces the search parameters from the next leaf batch on (games keep running)."""
+        sr = AzSearchParams(0.0, 0.0, 1, 1, 0, 0)  # c_puct_base <= 0: keep the current search parameters
+        if search is not None:
+            sr = AzSearchParams(float(search.get('c_puct_base', 19652.0)), float(search.get('c_puct_init', 1.25)), int(search['num_simulations']),
+                                int(search['num_parallel']), int(bool(search.get('root_noise', True))), int(bool(search.get('deterministic', False))))
+        sp = AzSelfplayParams(sr, int(warm_up_steps), int(check_resign_after_steps), float(resign_threshold), float(disable_resign_ratio))
         self.b.check(self.b.dll.az_selfplay_update(self.h, C.byref(sp)))
+
+    def selfplay_restart(self, slots):
+        """Abandon the games running in `slots` (nothing emitted) and start new ones there; call between ticks."""
+        s = i32(slots).ravel()
+        if s.size:
+            self.b.check(self.b.dll.az_selfplay_restart(self.h, as_ptr(s, C.c_int32), s.size))
 
     def selfplay_tick(self, n=1):
         self.b.check(self.b.dll.az_selfplay_tick(self.h, int(n)))

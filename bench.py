@@ -6,10 +6,17 @@
 
 Workload (BASELINE.json configs[1]): 9x9 Go, 4096 concurrent games per GPU, 400 simulations/move,
 num_parallel 8, AlphaZeroNet 10 blocks x 128 filters (fc 128), random-init weights (seed 123, BN
-statistics randomised), synthetic = self-play from empty boards.  One *step* = 51 leaf batches
-(ticks) = (400+8)/8, i.e. about one move of every game: select -> network -> expand/backup ->
-move / re-root / recycle, all on the device.  A *simulation* is one root-visit increment
-(SURVEY.md 8d); the count comes from the engine's device counters.
+statistics randomised), synthetic = self-play games produced by the engine itself.  One *step* = 51
+leaf batches (ticks) = (400+8)/8, i.e. about one move of every game: select -> network ->
+expand/backup -> move / re-root / recycle, all on the device.  A *simulation* is one root-visit
+increment; the count comes from the engine's device counters.
+
+Population: a self-play fleet in steady state holds games of every age, and finished games leave the
+device every step.  A cold start (all games at move 0) never sees a game end inside a short window, so
+before the warm-up steps the bench plays a cheap prologue (num_simulations = num_parallel, two ticks
+per move) and restarts slot g after (g mod L) prologue moves (az_selfplay_restart): the timed steps then
+run on games aged 0..L-1 plies, with finished games drained and all-gathered inside the e2e region.
+`--cold-start` skips the prologue (the round's earlier numbers were taken that way).
 
 Timing: W untimed warm-up steps, then K steps bracketed by barrier + synchronize, CUDA events on
 the engine's own stream, max over ranks.  Every tick streams a ~2.5 GB working set (activations of
@@ -36,6 +43,25 @@ WORKLOADS = {
     'go19_c5': ('go', 19, 128, 800, 8, 19, 256, 256, 30, 80),
     'go9_tiny': ('go', 9, 256, 64, 8, 2, 64, 64, 8, 20),
 }
+# prologue length L (plies) of the age stagger: about the length of a random-init game of the workload
+STAGGER = {'go9_c2': 128, 'gomoku13_c4': 64, 'go19_c5': 256, 'go9_tiny': 96}
+
+
+def stagger_population(eng, G, L, par, warm, chk, sims):
+    """Age the freshly begun population: L cheap moves (num_simulations = num_parallel), slot g restarted after g mod L of them,
+    then the workload's search parameters are switched in and whatever finished during the prologue is discarded."""
+    import numpy as np
+
+    slots = np.arange(G, dtype=np.int32)
+    ticks_fast = (par + par + par - 1) // par
+    for m in range(L):
+        eng.selfplay_tick(ticks_fast)
+        eng.selfplay_restart(slots[slots % L == m])
+    eng.selfplay_update(warm, chk, -1.0, 1.0, search=dict(num_simulations=sims, num_parallel=par))
+    while True:
+        games, st, pis, zs = eng.drain_games()
+        if not games:
+            break
 
 
 def make_net(game, n, nb, nf, fc):
@@ -219,6 +245,7 @@ def main():
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--games', type=int, default=0, help='override games per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cold-start', action='store_true', help='all games start at move 0 (no age stagger)')
     a = ap.parse_args()
     if a.impl == 'reference':
         return reference_arm(a)
@@ -248,20 +275,33 @@ def main():
     eng = Engine(game, n, num_games=G, max_simulations=sims, max_parallel=par, net=(nb, nf, fc), precision=a.precision, device=local, seed=1 + rank)
     eng.set_weights(pinned)
     stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device('cuda', local))
-    eng.selfplay_begin(sims, par, warm_up_steps=warm, check_resign_after_steps=chk, resign_threshold=-1.0, disable_resign_ratio=1.0)
+    L = 0 if a.cold_start else min(STAGGER[a.workload], max(1, G))
+    if L:
+        eng.selfplay_begin(par, par, warm_up_steps=warm, check_resign_after_steps=chk, resign_threshold=-1.0, disable_resign_ratio=1.0)
+        stagger_population(eng, G, L, par, warm, chk, sims)
+    else:
+        eng.selfplay_begin(sims, par, warm_up_steps=warm, check_resign_after_steps=chk, resign_threshold=-1.0, disable_resign_ratio=1.0)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    backlog = []
+
     def gather_samples(states, pis, zs):
-        """NCCL all-gather of the (state, pi, z) samples produced this step: fixed-capacity blocks + counts."""
+        """NCCL all-gather of the (state, pi, z) samples produced this step: fixed-capacity blocks + counts; what
+        does not fit the block waits for the next step."""
         if dist is None:
             return len(zs)
         from alpha_zero_b200.gather import all_gather_samples
 
-        S, P, Z, _ = all_gather_samples(states, pis, zs, capacity=G * 2, device=f'cuda:{local}')
+        if backlog:
+            b = backlog.pop()
+            states, pis, zs = np.concatenate([b[0], states]), np.concatenate([b[1], pis]), np.concatenate([b[2], zs])
+        S, P, Z, kept = all_gather_samples(states, pis, zs, capacity=G * 2, device=f'cuda:{local}')
+        if kept:
+            backlog.append((states[-kept:], pis[-kept:], zs[-kept:]))
         return len(Z)
 
     # ---- warm-up --------------------------------------------------------------------------------
@@ -286,7 +326,7 @@ def main():
     tower_ms, tower_evals = eng.last_net_ms()
 
     # ---- end to end through the public API with host buffers: `e2e` ----------------------------
-    d2h_bytes, gathered = 0, 0
+    d2h_bytes, gathered, e2e_games, e2e_len = 0, 0, 0, 0
     barrier()
     t0 = time.perf_counter()
     ce0 = eng.counters()
@@ -296,6 +336,8 @@ def main():
         games, st, pis, zs = eng.drain_games()  # device -> host: finished games' (state, pi, z)
         ce = eng.counters()  # device -> host: the step's result counters
         d2h_bytes += st.nbytes + pis.nbytes + zs.nbytes + 12 * 8
+        e2e_games += len(games)
+        e2e_len += sum(g['game_length'] for g in games)
         gathered += gather_samples(st, pis, zs)
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -319,6 +361,7 @@ def main():
     e2e_max = allmax(e2e_s)
     d = {k: allsum(float(c1[k] - c0[k])) for k in ('simulations', 'evaluations', 'moves', 'games', 'descents', 'depth_sum')}
     e2e_sims = allsum(float(ce1['simulations'] - ce0['simulations']))
+    e2e_games_all, e2e_len_all = allsum(float(e2e_games)), allsum(float(e2e_len))
     launches = c1['kernel_launches'] - c0['kernel_launches']
     errors = allsum(float(c1['errors']))
 
@@ -348,12 +391,15 @@ def main():
             'ms_per_step': ms_max / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': a.precision if a.precision != 'fp32' else 'f32', 'data': 'synthetic',
             'config': {'workload': f'{a.workload}: {n}x{n} {game}, {G} concurrent games per GPU, {sims} sims/move, num_parallel {par}, net {nb}x{nf} fc{fc} '
-                                   f'(random init seed 123); step = {ticks} leaf batches; working set >> L2 (no flush needed)',
+                                   f'(random init seed 123); step = {ticks} leaf batches; ' + (f'game ages staggered over 0..{L - 1} plies by a cheap prologue' if L else 'cold start: all games at move 0')
+                                   + '; working set >> L2 (no flush needed)',
                        'games_per_gpu': G, 'parallelism': f'games sharded, {world} process(es), NCCL all-gather of samples only'},
             'evals_per_sec': d['evaluations'] / (ms_max * 1e-3), 'moves_per_sec': d['moves'] / (ms_max * 1e-3),
-            'games_finished_in_window': d['games'], 'mean_leaf_depth': d['depth_sum'] / max(1.0, d['descents']), 'device_errors': errors,
+            'games_per_sec': d['games'] / (ms_max * 1e-3), 'games_finished_in_window': d['games'], 'mean_leaf_depth': d['depth_sum'] / max(1.0, d['descents']), 'device_errors': errors,
             'e2e': {'value': e2e_sims / e2e_max, 'unit': 'simulations/s', 'h2d_bytes_per_step': int(eng.weight_bytes),
-                    'd2h_bytes_per_step': int(d2h_bytes / max(1, a.steps)), 'samples_all_gathered': gathered},
+                    'd2h_bytes_per_step': int(d2h_bytes / max(1, a.steps)), 'samples_all_gathered': gathered,
+                    'games_drained': e2e_games_all, 'games_per_sec': e2e_games_all / e2e_max,
+                    'mean_game_length': e2e_len_all / max(1.0, e2e_games_all)},
             'gpu_launches': int(launches),
             'roofline': {'bound': 'tensor', 'kernel': ('k_conv_tc_halo' if nf <= 128 and os.environ.get('AZ_TC_MODE', '2') != '0' else 'k_conv_tc') if a.precision == 'bf16' else 'k_conv_f32', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                          'frac': (achieved / peak) if achieved else None, 'traffic': traffic, 'traffic_unit': 'bytes per launch (ncu dram__bytes_read+write)',

@@ -178,8 +178,17 @@ int az_search_run(az_engine* e);
 int az_selfplay_begin(az_engine* e, const az_selfplay_params* p);
 int az_selfplay_tick(az_engine* e, int32_t n_ticks);
 /* Change warm-up / resignation knobs of the running loop without resetting the games
- * (var_resign_threshold is re-read before every game, core/pipeline.py:241-246). */
+ * (var_resign_threshold is re-read before every game, core/pipeline.py:241-246).  When p->search.c_puct_base > 0 the
+ * search parameters (num_simulations, num_parallel, c_puct_*, root_noise, deterministic) are replaced as well, effective
+ * from the next leaf batch: searches in flight simply run to the new bound (the reference reads FLAGS.num_simulations /
+ * num_parallel once per actor, core/pipeline.py:166-189; a restarted actor picks up new ones).  c_puct_base <= 0 keeps
+ * the current search parameters. */
 int az_selfplay_update(az_engine* e, const az_selfplay_params* p);
+/* Abandon the games running in `slots` and start new ones there: nothing is emitted for the abandoned games (no samples,
+ * no record) — what happens to the game in flight when one of the reference's actor processes is restarted
+ * (training_go.py:318-330 spawns them, core/pipeline.py:227 is their game loop).  Must be called between ticks.  bench.py
+ * uses it once to stagger the ages of a freshly begun population so that the timed window sees games finishing. */
+int az_selfplay_restart(az_engine* e, const int32_t* slots, int32_t n);
 int az_sync(az_engine* e);
 int az_get_counters(az_engine* e, az_counters* out);
 /* Drain finished games: up to max_games records and their samples, oldest first.

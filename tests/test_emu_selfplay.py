@@ -96,3 +96,73 @@ def test_selfplay_loop_produces_valid_games(emu, game):
     else:
         assert n_resign == 0
     eng.close()
+
+
+def test_restart_and_search_update_keep_the_loop_consistent(emu):
+    """az_selfplay_restart abandons games without emitting anything; az_selfplay_update with search parameters changes the
+    simulations per move of the running loop.  Every game that does finish is still a complete, legal game from the empty board."""
+    max_steps = 30
+    eng = Engine('go', 9, num_games=10, max_simulations=32, max_parallel=4, net=(1, 16, 16), precision='fp32', max_steps=max_steps, seed=5,
+                 sample_ring=900, binding=emu)
+    eng.set_weights(_dummy_weights(1, 16, 16, 17, 82, 81))
+    with pytest.raises(Exception):
+        eng.selfplay_restart([0])  # loop not begun
+    eng.selfplay_begin(8, 4, warm_up_steps=4, check_resign_after_steps=8, resign_threshold=-1.0, disable_resign_ratio=1.0)
+    ticks_per_move = (8 + 4 + 3) // 4
+    uids, n_games, total = set(), 0, 0
+    restarted_at = {}
+    for mv in range(24):  # stagger: slot g restarts after (g % 8) * 3 moves
+        eng.selfplay_tick(ticks_per_move)
+        if mv % 3 == 0:
+            sl = [g for g in range(10) if (g % 8) * 3 == mv]
+            eng.selfplay_restart(sl)
+            for g in sl:
+                restarted_at[g] = mv
+    with pytest.raises(ValueError):
+        eng.selfplay_restart([1, 1])
+    c0 = eng.counters()
+    assert c0['errors'] == 0
+    # the slots now differ in age: the per-slot ply counters say so
+    steps = [eng.env_scalars(g)['steps'] for g in range(10)]
+    assert len(set(steps)) >= 5, steps
+    # more simulations per move from here on
+    eng.selfplay_update(4, 8, -1.0, 1.0, search=dict(num_simulations=24, num_parallel=4))
+    for rnd in range(40):
+        eng.selfplay_tick(7)
+        games, states, pis, zs = eng.drain_games()
+        for rec in games:
+            total += _check_game('go', rec, states, pis, zs, eng.last_moves, max_steps)
+            assert rec['reserved'] not in uids
+            uids.add(rec['reserved'])
+            n_games += 1
+    c1 = eng.counters()
+    assert c1['errors'] == 0 and c1['ring_dropped'] == 0
+    assert c1['games'] == n_games and c1['samples'] == total and n_games >= 10
+    sims_per_move = (c1['simulations'] - c0['simulations']) / max(1, c1['moves'] - c0['moves'])
+    assert 20.0 < sims_per_move < 30.0, sims_per_move  # 24 + num_parallel bound, minus carried visits
+    eng.close()
+
+
+def test_bench_population_stagger(emu):
+    """bench.py's prologue: after it the slots hold games of every age 0..L-1 (or younger, where a game ended on its own), nothing is
+    left in the rings, and the loop runs on with the workload's search parameters."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    G, L = 24, 12
+    eng = Engine('go', 9, num_games=G, max_simulations=32, max_parallel=4, net=(1, 16, 16), precision='fp32', max_steps=40, seed=9,
+                 sample_ring=2000, binding=emu)
+    eng.set_weights(_dummy_weights(1, 16, 16, 17, 82, 81))
+    eng.selfplay_begin(4, 4, warm_up_steps=4, check_resign_after_steps=8, resign_threshold=-1.0, disable_resign_ratio=1.0)
+    bench.stagger_population(eng, G, L, 4, 4, 8, 16)
+    steps = np.array([eng.env_scalars(g)['steps'] for g in range(G)])
+    want = L - 1 - (np.arange(G) % L)  # slot g restarted after (g mod L) + 1 of the L prologue moves
+    assert np.all(steps <= want + 1) and np.all(steps[want > 2] > 0), (steps, want)
+    assert len(set(steps.tolist())) >= L // 2
+    assert eng.drain_games()[0] == []
+    c0 = eng.counters()
+    eng.selfplay_tick(40)
+    c1 = eng.counters()
+    spm = (c1['simulations'] - c0['simulations']) / max(1, c1['moves'] - c0['moves'])
+    assert c1['errors'] == 0 and 12.0 < spm < 21.0, spm
+    eng.close()

@@ -193,6 +193,39 @@ def test_selfplay_device_loop(cuda):
     eng.close()
 
 
+def test_selfplay_restart_and_population_stagger(cuda):
+    """az_selfplay_restart / az_selfplay_update(search=...) on the CUDA library: bench.py's prologue leaves games of every age, and
+    every game finished afterwards is a complete legal game from the empty board (no plies of abandoned games leak into records)."""
+    import bench
+    from alpha_zero_b200.engine import Engine
+    from test_emu_selfplay import _check_game
+
+    z, n, a, nb, nf, fc, gomoku, net = _net_case('go9_small')
+    G, L = 96, 24
+    eng = Engine('go', 9, num_games=G, max_simulations=32, max_parallel=4, net=(nb, nf, fc), precision='fp32', max_steps=40, seed=9)
+    eng.set_weights(net.state_dict())
+    eng.selfplay_begin(4, 4, warm_up_steps=4, check_resign_after_steps=8, resign_threshold=-1.0, disable_resign_ratio=1.0)
+    bench.stagger_population(eng, G, L, 4, 4, 8, 24)
+    steps = np.array([eng.env_scalars(g)['steps'] for g in range(G)])
+    want = L - 1 - (np.arange(G) % L)
+    assert np.all(steps <= want + 1) and len(set(steps.tolist())) >= L // 2, (steps, want)
+    assert eng.drain_games()[0] == []
+    c0 = eng.counters()
+    uids, n_games = set(), 0
+    for rnd in range(30):
+        eng.selfplay_tick(8)
+        games, states, pis, zs = eng.drain_games()
+        for rec in games:
+            _check_game('go', rec, states, pis, zs, eng.last_moves, 40)
+            assert rec['reserved'] not in uids
+            uids.add(rec['reserved'])
+            n_games += 1
+    c1 = eng.counters()
+    spm = (c1['simulations'] - c0['simulations']) / max(1, c1['moves'] - c0['moves'])
+    assert c1['errors'] == 0 and c1['ring_dropped'] == 0 and n_games > G // 2 and 18.0 < spm < 29.0, (c1, n_games, spm)
+    eng.close()
+
+
 def _check_games(games, states, zs):
     for g in games:
         s0, ln = g['first_sample'], g['game_length']
