@@ -55,7 +55,7 @@ SYMBOLS = [
     'az_env_board', 'az_env_scalars', 'az_env_score', 'az_env_copy', 'az_env_state_bytes', 'az_env_export',
     'az_env_import', 'az_env_replay', 'az_search_begin', 'az_search_select', 'az_search_apply', 'az_search_result', 'az_search_commit',
     'az_search_run', 'az_selfplay_begin', 'az_selfplay_tick', 'az_selfplay_update', 'az_selfplay_restart', 'az_sync', 'az_get_counters', 'az_drain_games',
-    'az_sample_ring_device', 'az_stream', 'az_last_net_ms', 'az_replay_create', 'az_replay_ingest', 'az_replay_add', 'az_replay_info',
+    'az_sample_ring_device', 'az_stream', 'az_last_net_ms', 'az_tick_profile', 'az_replay_create', 'az_replay_ingest', 'az_replay_add', 'az_replay_info',
     'az_replay_sample',
 ]
 

@@ -39,10 +39,40 @@ struct az_engine {
   int rp_batch_cap = 0;
   float last_net_ms = 0.f;
   int last_net_evals = 0;
+  // az_tick_profile: per-phase device time of the self-play tick, CUDA events on the engine stream
+  bool prof_on = false;
+  double prof_ms[5] = {0, 0, 0, 0, 0};  // collect+compact, network, apply, advance, whole tick
+  int prof_ticks = 0;
 #ifndef AZ_EMU
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool collect_occ = false;             // AZ_COLLECT_OCC=1: k_collect built for 7 CTAs per SM (one wave for 4096 games)
+  std::vector<cudaEvent_t> prof_ev;     // 5 per tick of the last az_selfplay_tick call
+  int prof_pending = 0;                 // ticks recorded and not yet folded into prof_ms
 #endif
 };
+
+static void launch_collect(az_engine* e) {
+  const AzDims& d = e->E.d;
+#ifndef AZ_EMU
+  if (e->collect_occ) { AZ_LAUNCH_WARPS(e->rt, k_collect_occ, d.G, d, e->E); return; }
+#endif
+  AZ_LAUNCH_WARPS(e->rt, k_collect, d.G, d, e->E);
+}
+
+#ifndef AZ_EMU
+static void prof_fold(az_engine* e) {
+  if (!e->prof_pending) return;
+  cudaStreamSynchronize(e->rt.stream);
+  for (int t = 0; t < e->prof_pending; ++t) {
+    float ms = 0.f;
+    for (int k = 0; k < 4; ++k)
+      if (cudaEventElapsedTime(&ms, e->prof_ev[(size_t)t * 5 + k], e->prof_ev[(size_t)t * 5 + k + 1]) == cudaSuccess) e->prof_ms[k] += ms;
+    if (cudaEventElapsedTime(&ms, e->prof_ev[(size_t)t * 5], e->prof_ev[(size_t)t * 5 + 4]) == cudaSuccess) e->prof_ms[4] += ms;
+  }
+  e->prof_ticks += e->prof_pending;
+  e->prof_pending = 0;
+}
+#endif
 
 template <class T>
 static T* dev_alloc(az_engine* e, size_t count) {
@@ -189,6 +219,10 @@ extern "C" int az_create(const az_config* cfg, az_engine** out) {
 #ifndef AZ_EMU
   cudaEventCreate(&e->ev0);
   cudaEventCreate(&e->ev1);
+  {
+    const char* oc = getenv("AZ_COLLECT_OCC");
+    e->collect_occ = oc && atoi(oc) != 0;
+  }
 #endif
   // every slot starts as a freshly reset game
   std::vector<int32_t> all(G);
@@ -209,6 +243,7 @@ extern "C" int az_destroy(az_engine* e) {
 #ifndef AZ_EMU
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
+  for (cudaEvent_t ev : e->prof_ev) cudaEventDestroy(ev);
 #endif
   rt_destroy(e->rt);
   delete e;
@@ -482,7 +517,7 @@ extern "C" int az_search_begin(az_engine* e, const int32_t* slots, const int32_t
 
 static int collect_and_compact(az_engine* e, int32_t tot[2]) {
   const AzDims& d = e->E.d;
-  AZ_LAUNCH_WARPS(e->rt, k_collect, d.G, d, e->E);
+  launch_collect(e);
 #ifdef AZ_EMU
   e->rt.launches++;
   k_compact(e->E, d.G);
@@ -633,8 +668,23 @@ extern "C" int az_selfplay_tick(az_engine* e, int32_t n_ticks) {
   if (!e) return az_fail(AZ_ERR_BAD_ARG, "null engine");
   if (!e->selfplay) return az_fail(AZ_ERR_STATE, "az_selfplay_tick: call az_selfplay_begin first");
   const AzDims& d = e->E.d;
+#ifndef AZ_EMU
+  const bool prof = e->prof_on;
+  if (prof) {
+    prof_fold(e);
+    while (e->prof_ev.size() < (size_t)n_ticks * 5) {
+      cudaEvent_t ev;
+      if (cudaEventCreate(&ev) != cudaSuccess) return az_fail(AZ_ERR_CUDA, "az_selfplay_tick: cudaEventCreate failed");
+      e->prof_ev.push_back(ev);
+    }
+  }
+#define AZ_PROF_MARK(k) do { if (prof) cudaEventRecord(e->prof_ev[(size_t)t * 5 + (k)], e->rt.stream); } while (0)
+#else
+#define AZ_PROF_MARK(k) do { } while (0)
+#endif
   for (int t = 0; t < n_ticks; ++t) {
-    AZ_LAUNCH_WARPS(e->rt, k_collect, d.G, d, e->E);
+    AZ_PROF_MARK(0);
+    launch_collect(e);
 #ifndef AZ_EMU
     e->rt.launches++;
     k_compact<<<1, 1024, 0, e->rt.stream>>>(e->E, d.G);
@@ -642,14 +692,24 @@ extern "C" int az_selfplay_tick(az_engine* e, int32_t n_ticks) {
 #else
     k_compact(e->E, d.G);
 #endif
+    AZ_PROF_MARK(1);
     int rc = aznet_forward(e->net, e->rt, e->E.leaf_obs, e->E.leaf_rows, e->E.leaf_total, d.G * d.Pmax, e->E.priors, e->E.values, d.Ap);
     if (rc) return az_fail(rc, "network forward: " + g_az_error);
 #ifndef AZ_EMU
     if (t == n_ticks - 1) cudaEventRecord(e->ev1, e->rt.stream);
 #endif
+    AZ_PROF_MARK(2);
     AZ_LAUNCH_WARPS(e->rt, k_apply, d.G, d, e->E);
+    AZ_PROF_MARK(3);
     AZ_LAUNCH_WARPS(e->rt, k_advance, d.G, d, e->E);
+    AZ_PROF_MARK(4);
   }
+#undef AZ_PROF_MARK
+#ifndef AZ_EMU
+  if (prof) e->prof_pending = n_ticks;
+#else
+  if (e->prof_on) e->prof_ticks += n_ticks;
+#endif
 #ifndef AZ_EMU
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return az_fail(AZ_ERR_CUDA, std::string("CUDA launch error: ") + cudaGetErrorString(ce));
@@ -777,6 +837,19 @@ extern "C" int az_last_net_ms(az_engine* e, float* ms, int32_t* n_evals) {
   *ms = 0.f;
   if (n_evals) *n_evals = 0;
 #endif
+  return AZ_OK;
+}
+
+extern "C" int az_tick_profile(az_engine* e, int32_t enable, double* ms5, int32_t* n_ticks) {
+  if (!e) return az_fail(AZ_ERR_BAD_ARG, "null engine");
+#ifndef AZ_EMU
+  prof_fold(e);
+#endif
+  if (ms5) for (int k = 0; k < 5; ++k) ms5[k] = e->prof_ms[k];
+  if (n_ticks) *n_ticks = e->prof_ticks;
+  for (int k = 0; k < 5; ++k) e->prof_ms[k] = 0.0;
+  e->prof_ticks = 0;
+  e->prof_on = enable != 0;
   return AZ_OK;
 }
 

@@ -69,6 +69,20 @@ AZ_GLOBAL k_collect(AzState E, int nwarps) {
   }
 }
 
+#ifndef AZ_EMU
+// Same kernel compiled for 7 CTAs (28 warps) per SM: 4096 games then fit in ONE wave on 148 SMs (the unconstrained build
+// allocates 96 registers -> 5 CTAs per SM -> 2960 resident warps, i.e. a 1.4-wave launch).  Chosen with AZ_COLLECT_OCC=1.
+__global__ void __launch_bounds__(AZ_WPB * 32, 7) k_collect_occ(AzState E, int nwarps) {
+  AZ_WARP_INDEX(nwarps) {
+    Sim S;
+    AZ_SCRATCH(E.d, S);
+    LocalCounters lc = {0, 0, 0, 0, 0, 0};
+    game_collect(E, az_g, S, lc);
+    flush_counters(E, lc);
+  }
+}
+#endif
+
 AZ_GLOBAL k_apply(AzState E, int nwarps) {
   AZ_WARP_INDEX(nwarps) {
     LocalCounters lc = {0, 0, 0, 0, 0, 0};

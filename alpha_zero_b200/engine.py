@@ -283,6 +283,14 @@ class Engine:
         self.b.check(self.b.dll.az_stream(self.h, C.byref(p)))
         return p.value
 
+    def tick_profile(self, enable):
+        """Per-phase device time (ms) accumulated since the last call, then switch the per-tick event recording on / off."""
+        ms = (C.c_double * 5)()
+        n = C.c_int32()
+        self.b.check(self.b.dll.az_tick_profile(self.h, int(bool(enable)), ms, C.byref(n)))
+        keys = ('select', 'network', 'expand_backup', 'move_reroot', 'tick')
+        return {k: float(v) for k, v in zip(keys, ms)}, int(n.value)
+
     def last_net_ms(self):
         ms, n = C.c_float(), C.c_int32()
         self.b.check(self.b.dll.az_last_net_ms(self.h, C.byref(ms), C.byref(n)))

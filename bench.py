@@ -343,6 +343,12 @@ def main():
     e2e_s = time.perf_counter() - t0
     ce1 = eng.counters()
 
+    # ---- per-phase split of the tick (one extra, untimed step with CUDA events around every phase) ----
+    eng.tick_profile(True)
+    eng.selfplay_tick(ticks)
+    eng.sync()
+    phase_ms, phase_ticks = eng.tick_profile(False)
+
     def allmax(x):
         if dist is None:
             return x
@@ -407,6 +413,9 @@ def main():
                          'note': f'algorithmic 2*MAC of one 3x3 conv layer ({conv_flops_per_eval / 1e6:.1f} MFLOP/leaf) x {tower_evals} leaves / mean launch time over the '
                                  f'{n_conv} tower launches of the last tick ({tower_ms:.3f} ms, CUDA events on the engine stream)'},
             'clocks': clk.summary(),
+            'tick_breakdown_ms': dict({k: v / max(1, phase_ticks) for k, v in phase_ms.items()}, ticks=phase_ticks,
+                                      note='mean device time per tick of one extra step, CUDA events around each phase (az_tick_profile); '
+                                           'select = k_collect + k_compact, network = input + tower + heads, expand_backup = k_apply, move_reroot = k_advance'),
         }
         if world == 1 and not a.no_cpu_baseline:
             secs = float(os.environ.get('AZ_CPU_SECONDS', '15'))

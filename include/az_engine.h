@@ -203,6 +203,13 @@ int az_stream(az_engine* e, void** cuda_stream);
 /* Time of the network kernels of the most recent az_selfplay_tick call, measured with CUDA events (ms). */
 int az_last_net_ms(az_engine* e, float* ms, int32_t* n_evals);
 
+/* Per-phase device time of the self-play tick, for the measurement tooling (bench.py `tick_breakdown_ms`): with profiling
+ * enabled every tick records CUDA events on the engine stream around its phases.  The call returns the times accumulated
+ * since the previous call — ms5 = {select (k_collect + k_compact), network, expand/backup (k_apply), move/re-root
+ * (k_advance), whole tick} over *n_ticks ticks — resets the accumulators and sets the switch to `enable`.  Off by default:
+ * the timed regions of bench.py run without it. */
+int az_tick_profile(az_engine* e, int32_t enable, double* ms5, int32_t* n_ticks);
+
 /* ---- device-resident replay: the learner's input path -------------------------------
  * UniformReplay (core/replay.py:35-116) with the storage in HBM: az_replay_ingest == add_game for every finished
  * game, moved from the sample ring device-to-device (games taken here are no longer returned by az_drain_games);

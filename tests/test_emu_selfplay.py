@@ -161,7 +161,9 @@ def test_bench_population_stagger(emu):
     assert len(set(steps.tolist())) >= L // 2
     assert eng.drain_games()[0] == []
     c0 = eng.counters()
+    assert eng.tick_profile(True) == ({'select': 0.0, 'network': 0.0, 'expand_backup': 0.0, 'move_reroot': 0.0, 'tick': 0.0}, 0)
     eng.selfplay_tick(40)
+    assert eng.tick_profile(False)[1] == 40  # the emulation build has no device clock: it only counts the profiled ticks
     c1 = eng.counters()
     spm = (c1['simulations'] - c0['simulations']) / max(1, c1['moves'] - c0['moves'])
     assert c1['errors'] == 0 and 12.0 < spm < 21.0, spm

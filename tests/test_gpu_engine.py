@@ -223,6 +223,14 @@ def test_selfplay_restart_and_population_stagger(cuda):
     c1 = eng.counters()
     spm = (c1['simulations'] - c0['simulations']) / max(1, c1['moves'] - c0['moves'])
     assert c1['errors'] == 0 and c1['ring_dropped'] == 0 and n_games > G // 2 and 18.0 < spm < 29.0, (c1, n_games, spm)
+    # az_tick_profile: phases are timed on the device and add up to the tick
+    eng.tick_profile(True)
+    eng.selfplay_tick(6)
+    ms, nt = eng.tick_profile(False)
+    parts = ms['select'] + ms['network'] + ms['expand_backup'] + ms['move_reroot']
+    assert nt == 6 and all(v > 0 for v in ms.values()) and abs(parts - ms['tick']) < 0.05 * ms['tick'] + 0.05, ms
+    eng.selfplay_tick(2)
+    assert eng.tick_profile(False)[1] == 0  # switched off again
     eng.close()
 
 
