@@ -314,6 +314,7 @@ AZ_DEV StepOut go_play(const AzDims& d, Sim& S, int action) {
       memcpy(keep, S.label, (size_t)d.nc * 2);
       go_label(d, S, false);
       if (memcmp(keep, S.label, (size_t)d.nc * 2) != 0) { fprintf(stderr, "incremental group labels diverged\n"); abort(); }
+      S.libs_valid = 0;  // go_label used aux[] as its scratch: the liberty counts have to be rebuilt before go_legal reads them
     }
 #endif
     S.ko = (cnt == 1 && koish == -mover) ? capcell : -1;  // go_engine.py:491-494

@@ -14,6 +14,10 @@
 
 thread_local std::string g_az_error;
 
+#ifndef AZ_NODE_CACHE_DEFAULT
+#define AZ_NODE_CACHE_DEFAULT 1
+#endif
+
 struct az_engine {
   az_config cfg;
   AzRt rt;
@@ -54,6 +58,11 @@ struct az_engine {
 static void launch_collect(az_engine* e) {
   const AzDims& d = e->E.d;
 #ifndef AZ_EMU
+  if (d.node_cache) {
+    if (e->collect_occ) AZ_LAUNCH_WARPS(e->rt, k_collect_nc_occ, d.G, d, e->E);
+    else AZ_LAUNCH_WARPS(e->rt, k_collect_nc, d.G, d, e->E);
+    return;
+  }
   if (e->collect_occ) { AZ_LAUNCH_WARPS(e->rt, k_collect_occ, d.G, d, e->E); return; }
 #endif
   AZ_LAUNCH_WARPS(e->rt, k_collect, d.G, d, e->E);
@@ -168,6 +177,18 @@ extern "C" int az_create(const az_config* cfg, az_engine** out) {
   E.root_p64 = dev_alloc<double>(e, G * d.Ap);
   E.noise = dev_alloc<double>(e, G * d.Ap);
   E.remap = dev_alloc<int16_t>(e, G * d.cap);
+  {
+    // per-node position cache (one ply per descent instead of a replay from the root): AZ_NODE_CACHE=0 switches it off
+    const char* nc = getenv("AZ_NODE_CACHE");
+    d.node_cache = nc ? (atoi(nc) != 0) : AZ_NODE_CACHE_DEFAULT;
+    E.nboard = nullptr; E.nlegal = nullptr; E.nko = nullptr;
+    if (d.node_cache) {
+      E.nboard = dev_alloc<int8_t>(e, nodes * d.ncp);
+      E.nlegal = dev_alloc<uint8_t>(e, nodes * d.Ap);
+      E.nko = dev_alloc<int16_t>(e, nodes);
+      if (!E.nko) { az_destroy(e); return az_fail(AZ_ERR_CUDA, "az_create: device allocation failed (node cache)"); }
+    }
+  }
   e->d_pbc_fresh = dev_alloc<double>(e, d.table_len);
   e->d_pbc_f32 = dev_alloc<double>(e, d.table_len);
   e->d_sqrt = dev_alloc<double>(e, d.table_len);
@@ -220,8 +241,9 @@ extern "C" int az_create(const az_config* cfg, az_engine** out) {
   cudaEventCreate(&e->ev0);
   cudaEventCreate(&e->ev1);
   {
+    // the node-cache kernel needs 108 registers unconstrained (4 CTAs per SM); built for 7 CTAs per SM it spills 16 bytes
     const char* oc = getenv("AZ_COLLECT_OCC");
-    e->collect_occ = oc && atoi(oc) != 0;
+    e->collect_occ = oc ? atoi(oc) != 0 : e->E.d.node_cache != 0;
   }
 #endif
   // every slot starts as a freshly reset game

@@ -64,6 +64,10 @@ AZ_GLOBAL k_collect(AzState E, int nwarps) {
     Sim S;
     AZ_SCRATCH(E.d, S);
     LocalCounters lc = {0, 0, 0, 0, 0, 0};
+#ifdef AZ_EMU
+    if (E.d.node_cache) game_collect_nc(E, az_g, S, lc);
+    else
+#endif
     game_collect(E, az_g, S, lc);
     flush_counters(E, lc);
   }
@@ -78,6 +82,25 @@ __global__ void __launch_bounds__(AZ_WPB * 32, 7) k_collect_occ(AzState E, int n
     AZ_SCRATCH(E.d, S);
     LocalCounters lc = {0, 0, 0, 0, 0, 0};
     game_collect(E, az_g, S, lc);
+    flush_counters(E, lc);
+  }
+}
+// Node-cache variants (d.node_cache): one ply per descent, see game_collect_nc.
+__global__ void k_collect_nc(AzState E, int nwarps) {
+  AZ_WARP_INDEX(nwarps) {
+    Sim S;
+    AZ_SCRATCH(E.d, S);
+    LocalCounters lc = {0, 0, 0, 0, 0, 0};
+    game_collect_nc(E, az_g, S, lc);
+    flush_counters(E, lc);
+  }
+}
+__global__ void __launch_bounds__(AZ_WPB * 32, 7) k_collect_nc_occ(AzState E, int nwarps) {
+  AZ_WARP_INDEX(nwarps) {
+    Sim S;
+    AZ_SCRATCH(E.d, S);
+    LocalCounters lc = {0, 0, 0, 0, 0, 0};
+    game_collect_nc(E, az_g, S, lc);
     flush_counters(E, lc);
   }
 }

@@ -68,6 +68,7 @@ struct AzDims {
   int table_len;     // length of the pb_c / sqrt tables
   int max_len;       // max plies per game (sample storage)
   int ring_cap;
+  int node_cache;    // 1: every tree node keeps its position (board, legal mask, ko) so that a descent plays ONE ply, at the leaf
 };
 
 struct AzSearchCfg {
@@ -103,6 +104,11 @@ struct AzState {
   double* root_p64;
   double* noise;       // [G][Ap] host-supplied Dirichlet samples
   int16_t* remap;      // [G][cap]
+  // per-node position cache (d.node_cache): the position AFTER the move that leads to the node, written when the node is first
+  // reached as a leaf; interior levels of a descent read the legal mask from here instead of replaying the game from the root
+  int8_t* nboard;      // [G][2][cap][ncp]
+  uint8_t* nlegal;     // [G][2][cap][Ap]
+  int16_t* nko;        // [G][2][cap]
   const double* pbc_fresh;  // log((1+n+cb)/cb)+ci, double arithmetic (fresh root)
   const double* pbc_f32;    // same with the quotient rounded to float32 (re-used root, inner nodes)
   const double* sqrt_tab;   // sqrt(n)
@@ -146,6 +152,8 @@ enum { CT_SIMS = 0, CT_EVALS, CT_MOVES, CT_GAMES, CT_NODES, CT_DEPTH, CT_DESCENT
 enum { GR_SLOT = 0, GR_LEN, GR_WINNER, GR_BY_RESIGN, GR_SCORE_BITS, GR_PASSES, GR_RESIGN_DISABLED, GR_MARKED_FOR_RESIGN,
        GR_COULD_WON, GR_MARKED_PLAYER, GR_FIRST_LO, GR_FIRST_HI, GR_UID, GR_INTS = 16 };
 #define AZ_GAMES_RING 4096
+#ifndef AZ_PATH
 #define AZ_PATH 64          // recorded path length; deeper leaves fall back to the serial parent walk
+#endif
 #define AZ_CIDX_EXPANDED 0x4000  // child link flag: the child is already expanded (saves a dependent load per level)
 #define AZ_CIDX_MASK 0x3FFF

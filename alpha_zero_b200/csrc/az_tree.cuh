@@ -25,6 +25,9 @@ struct TreeView {
   int16_t *parent, *pmove, *vloss;
   int8_t* to_play;
   uint8_t* expanded;
+  int8_t* nboard;   // per-node position cache (null unless d.node_cache)
+  uint8_t* nlegal;
+  int16_t* nko;
 };
 
 AZ_DEV TreeView tree_view(const AzState& E, int g, int buf) {
@@ -39,6 +42,9 @@ AZ_DEV TreeView tree_view(const AzState& E, int g, int buf) {
   T.vloss = E.nvloss + nb;
   T.to_play = E.nto_play + nb;
   T.expanded = E.expanded + nb;
+  T.nboard = E.nboard ? E.nboard + nb * E.d.ncp : nullptr;
+  T.nlegal = E.nlegal ? E.nlegal + nb * E.d.Ap : nullptr;
+  T.nko = E.nko ? E.nko + nb : nullptr;
   return T;
 }
 
@@ -407,6 +413,155 @@ AZ_DEV void game_collect(const AzState& E, int g, Sim& S, LocalCounters& lc) {
   w_sync();
 }
 
+// Observation of a leaf at `depth` in node-cache mode: the k-th most recent board is the scratch board (k = 0), the cached
+// board of the path node at depth-k, or - past the root - the slot's own history (envs/base.py:243-261).
+AZ_DEV void leaf_write_obs(const AzState& E, const TreeView& T, int g, const Sim& S, int node, int depth, int8_t* out) {
+  const AzDims& d = E.d;
+  int anc = node;  // node at depth - k while walking up (only used when the path was too deep to be recorded)
+  for (int k = 0; k < d.num_stack; ++k) {
+    const int j = depth - k;
+    const int8_t* b;
+    if (k == 0) b = S.board;
+    else if (j >= 1) {
+      if (depth <= AZ_PATH) anc = S.path_n[j - 1];
+      else anc = T.parent[anc];
+      b = T.nboard + (size_t)anc * d.ncp;
+    } else b = E.hist + ((size_t)g * 8 + (size_t)(-j)) * d.ncp;
+    int8_t* o0 = out + (size_t)(2 * k) * d.nc;
+    int8_t* o1 = o0 + d.nc;
+    W_FOR(c, d.nc) {
+      const int8_t v = b[c];
+      o0[c] = (v == S.to_play);
+      o1[c] = (v == -S.to_play);
+    }
+  }
+  int8_t* oc = out + (size_t)(2 * d.num_stack) * d.nc;
+  const int8_t colour = (S.to_play == 1);
+  W_FOR(c, d.nc) oc[c] = colour;
+  w_sync();
+}
+
+// game_collect with the per-node position cache (d.node_cache): interior levels of a descent only pick (the legal mask of an
+// expanded node is read from the cache); the game is advanced by ONE ply per descent, from the cached position of the leaf's
+// parent, and the new node's position is stored for the descents that will pass through it.  Same results as game_collect:
+// a node's position is a function of the path, so reading it back equals replaying it.
+AZ_DEV void game_collect_nc(const AzState& E, int g, Sim& S, LocalCounters& lc) {
+  const AzDims& d = E.d;
+  int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
+  const int st = ti[TI_STATE];
+  int nleaves = 0;
+  if (ti[TI_ACTIVE]) {
+    if (st == ST_NEED_ROOT) {
+      sim_load(E, g, S);
+      sim_write_obs(d, S, E.leaf_obs + (size_t)g * d.Pmax * d.obs_bytes);
+      W_LANE0 { E.leaf_node[(size_t)g * d.Pmax] = 0; E.leaf_depth[(size_t)g * d.Pmax] = 0; }
+      nleaves = 1;
+    } else if (st == ST_SEARCHING) {
+      TreeView T = tree_view(E, g, ti[TI_BUF]);
+      int n_nodes = ti[TI_NODES];
+      int tries = 0;
+      const int32_t* ei = E.env_i + (size_t)g * ENV_INTS;
+      const int r_to_play = ei[EI_TO_PLAY], r_steps = ei[EI_STEPS], r_h1 = ei[EI_H1], r_h2 = ei[EI_H2], r_ko = ei[EI_KO];
+      bool have_root_labels = false;
+      while (nleaves < E.s.P && tries < E.s.tries) {
+        tries++;
+        int node = 0, parent = 0, depth = 0, a = -1;
+        int prev1 = r_h1, prev2 = r_h2;  // the two moves before `node` (pass detection, go.py:176-192)
+        float n_cur = 0.f;
+        const uint8_t* legal = E.root_legal + (size_t)g * d.Ap;
+        bool aborted = false;
+        for (;;) {
+          int link;
+          float n_child;
+          a = tree_pick(E, T, g, node, legal, n_cur, link, n_child);
+          int child;
+          bool child_expanded = false;
+          if (link < 0) {
+            child = tree_new_node(E, T, node, a, ((depth + 1) & 1) ? -r_to_play : r_to_play, n_nodes, lc);
+            if (child < 0) { aborted = true; break; }
+            n_child = 0.f;
+          } else {
+            child = link & AZ_CIDX_MASK;
+            child_expanded = (link & AZ_CIDX_EXPANDED) != 0;
+          }
+          if (depth < AZ_PATH) {
+            W_LANE0 { S.path_k[depth] = node * d.Ap + a; S.path_n[depth] = (int16_t)child; }
+          }
+          parent = node;
+          node = child;
+          n_cur = n_child;
+          depth++;
+          if (!child_expanded) break;
+          prev2 = prev1;
+          prev1 = a;
+          legal = T.nlegal + (size_t)child * d.Ap;
+        }
+        if (aborted) break;
+        w_sync();
+        // ---- the position of `parent`, then the one ply that leads to the leaf
+        if (parent == 0) {
+          sim_load(E, g, S);
+          if (d.game == 0) {  // group labels of the root position: one full labelling per pass
+            if (!have_root_labels) {
+              go_label(d, S, false);
+              W_FOR(c, d.nc) S.root_label[c] = S.label[c];
+              have_root_labels = true;
+            } else {
+              W_FOR(c, d.nc) S.label[c] = S.root_label[c];
+            }
+            S.labels_valid = 1;
+            w_sync();
+          }
+        } else {
+          const int8_t* pb = T.nboard + (size_t)parent * d.ncp;
+          W_FOR(c, d.ncp) S.board[c] = pb[c];
+          S.to_play = ((depth - 1) & 1) ? -r_to_play : r_to_play;
+          S.steps = r_steps + depth - 1;
+          S.h1 = prev1;
+          S.h2 = prev2;
+          S.ko = T.nko[parent];
+          S.caps_b = S.caps_w = 0;  // capture totals are not part of the observation; the real game keeps its own (env_step)
+          S.head = 0;
+          S.labels_valid = 0;
+          S.libs_valid = 0;
+          w_sync();
+        }
+        const StepOut o = sim_play(d, S, a);
+        lc.descents++;
+        lc.depth += depth;
+        if (o.done) {  // terminal: never expanded, back up the game result (mcts_v2.py:604-608)
+          const float v = -(0.5f * (float)o.reward_x2);
+          if (depth <= AZ_PATH) path_backup(E, T, g, S.path_k, depth, v, lc);
+          else tree_backup(E, T, g, node, v, lc);
+          continue;
+        }
+        {  // remember the leaf's position for the descents that will go through it
+          int8_t* nb = T.nboard + (size_t)node * d.ncp;
+          W_FOR(c, d.ncp) nb[c] = S.board[c];
+          uint8_t* nl = T.nlegal + (size_t)node * d.Ap;
+          W_FOR(k, d.Ap) nl[k] = S.legal[k];
+          W_LANE0 T.nko[node] = (int16_t)S.ko;
+        }
+        if (E.s.use_vloss) {
+          if (depth <= AZ_PATH) path_vloss(E, T, g, S.path_k, S.path_n, depth, +1);
+          else tree_vloss(E, T, g, node, +1);
+        }
+        const size_t row = (size_t)g * d.Pmax + nleaves;
+        W_LANE0 { E.leaf_node[row] = (int16_t)node; E.leaf_depth[row] = depth; }
+        if (depth <= AZ_PATH) {
+          W_FOR(i, depth) { E.leaf_pk[row * AZ_PATH + i] = S.path_k[i]; E.leaf_pn[row * AZ_PATH + i] = S.path_n[i]; }
+        }
+        leaf_write_obs(E, T, g, S, node, depth, E.leaf_obs + row * d.obs_bytes);
+        nleaves++;
+      }
+      W_LANE0 ti[TI_NODES] = n_nodes;
+    }
+  }
+  W_LANE0 ti[TI_NLEAVES] = nleaves;
+  lc.evals += nleaves;
+  w_sync();
+}
+
 // Consume the evaluator's output for slot g (mcts_v2.py:364-368, :613-625).
 AZ_DEV void game_apply(const AzState& E, int g, LocalCounters& lc) {
   const AzDims& d = E.d;
@@ -492,6 +647,11 @@ AZ_DEV int game_commit(const AzState& E, int g, int move, double* best_child_q) 
         if (has) { remap[ni] = (int16_t)(c & AZ_CIDX_MASK); Tn.parent[ni] = (int16_t)i; Tn.pmove[ni] = (int16_t)a; }
         Tn.cidx[(size_t)i * Ap + a] = has ? (int16_t)(ni | (c & AZ_CIDX_EXPANDED)) : (int16_t)-1;
         base += az_popc(m);
+      }
+      if (To.nboard) {  // the node's cached position moves with it
+        W_FOR(c, d.ncp) Tn.nboard[(size_t)i * d.ncp + c] = To.nboard[(size_t)old * d.ncp + c];
+        W_FOR(a, Ap) Tn.nlegal[(size_t)i * Ap + a] = To.nlegal[(size_t)old * Ap + a];
+        W_LANE0 Tn.nko[i] = To.nko[old];
       }
       count = base;
       W_LANE0 {

@@ -3,6 +3,7 @@
 // exercised without a GPU, this stub stands in for the evaluator with a deterministic hash of the observation:
 // priors = normalised pseudo-random weights, value = -0.88 / +0.88 (+- noise) for black / white to move, so that the
 // resignation branch is reached.  It is never part of the product library.
+#include <math.h>
 #include <stdlib.h>
 
 #include "az_net.h"
@@ -26,6 +27,11 @@ int aznet_set_weights(AzNet* n, AzRt&, const float* const*, const int64_t*, int,
 int aznet_forward(AzNet* n, AzRt&, const int8_t* obs_base, const int32_t* row_list, const int32_t* n_rows_dev, int max_rows,
                   float* priors_base, float* values_base, int pri_stride) {
   const int rows = *n_rows_dev < max_rows ? *n_rows_dev : max_rows;
+  // AZ_EMU_SHARP=k raises the pseudo-random prior weights to the k-th power: a peaked policy, hence deep, narrow trees
+  const char* sh = getenv("AZ_EMU_SHARP");
+  const double sharp = sh ? atof(sh) : 1.0;
+  const char* vs = getenv("AZ_EMU_VALUE_SCALE");  // < 1 flattens the values so that the (peaked) priors steer the search
+  const double vscale = vs ? atof(vs) : 1.0;
   for (int i = 0; i < rows; ++i) {
     const size_t row = row_list ? (size_t)row_list[i] : (size_t)i;
     const int8_t* o = obs_base + row * n->obs_bytes;
@@ -36,7 +42,8 @@ int aznet_forward(AzNet* n, AzRt&, const int8_t* obs_base, const int32_t* row_li
     for (int a = 0; a < n->A; ++a) {
       uint64_t z = h + (uint64_t)(a + 1) * 0x9E3779B97F4A7C15ull;
       z ^= z >> 29; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 32;
-      const double w = 1.0 + (double)(z % 1000);
+      double w = 1.0 + (double)(z % 1000);
+      if (sharp != 1.0) w = pow(w / 1000.0, sharp);
       p[a] = (float)w;
       sum += w;
     }
@@ -45,7 +52,7 @@ int aznet_forward(AzNet* n, AzRt&, const int8_t* obs_base, const int32_t* row_li
     // black's root and best-child values fall below any sensible resignation threshold, which exercises that branch
     const double u = (double)((h >> 16) % 20001) / 10000.0 - 1.0;  // [-1, 1]
     const bool black_to_play = o[n->obs_bytes - 1] != 0;
-    values_base[row] = (float)((black_to_play ? -0.88 : 0.88) + 0.1 * u);
+    values_base[row] = (float)(vscale * ((black_to_play ? -0.88 : 0.88) + 0.1 * u));
   }
   return 0;
 }

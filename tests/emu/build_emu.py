@@ -13,17 +13,21 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, 'alpha_zero_b200', 'csrc')
 OUT = os.path.join(HERE, 'libaz_emu.so')
+# 'deep': recorded path length 3, so that ordinary searches take the deeper-than-AZ_PATH fallbacks (serial parent walks for virtual
+# loss / backup / leaf history), and every incremental group relabelling is cross-checked against a full one (aborts on a mismatch)
+VARIANTS = {'': [], 'deep': ['-DAZ_PATH=3', '-DAZ_CHECK_LABELS']}
 
 
-def build(force=False):
+def build(force=False, variant=''):
+    out = OUT if not variant else os.path.join(HERE, f'libaz_emu_{variant}.so')
     srcs = [os.path.join(CSRC, 'az_engine.cu'), os.path.join(HERE, 'az_emu_net_stub.cpp')]
-    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.h', '.cuh'))]
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(p) for p in deps):
-        return OUT
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.h', '.cuh'))] + [os.path.abspath(__file__)]
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(p) for p in deps):
+        return out
     cmd = ['g++', '-std=c++17', '-O2', '-g', '-DAZ_EMU', '-ffp-contract=off', '-fPIC', '-shared', '-Wall', '-Wno-unused-function',
-           '-Wno-unused-variable', '-I', CSRC, '-I', os.path.join(ROOT, 'include'), '-x', 'c++', srcs[0], srcs[1], '-o', OUT]
+           '-Wno-unused-variable'] + VARIANTS[variant] + ['-I', CSRC, '-I', os.path.join(ROOT, 'include'), '-x', 'c++', srcs[0], srcs[1], '-o', out]
     subprocess.run(cmd, check=True)
-    return OUT
+    return out
 
 
 if __name__ == '__main__':

@@ -1,0 +1,84 @@
+"""Equivalence of the engine's internal variants on the host-emulation build (no GPU needed):
+
+* per-node position cache (AZ_NODE_CACHE, csrc/az_tree.cuh game_collect_nc) vs replaying every descent from the root:
+  identical self-play trajectories (the stub evaluator hashes the leaf observation, so one differing observation byte,
+  legal mask or visit count changes every later move), and the reference's MCTS traces / env corpus in both modes;
+* the 'deep' build (recorded path length 3 + group-label cross-check): the deeper-than-AZ_PATH fallbacks give the same
+  trajectories and pass the reference traces too.
+"""
+import ctypes
+import hashlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'emu'))
+import build_emu  # noqa: E402
+import enginecheck  # noqa: E402
+from alpha_zero_b200._lib import Binding  # noqa: E402
+from alpha_zero_b200.engine import Engine  # noqa: E402
+from test_emu_selfplay import _dummy_weights  # noqa: E402
+
+
+@pytest.fixture(scope='module')
+def libs():
+    return {v: Binding(ctypes.CDLL(build_emu.build(variant=v))) for v in ('', 'deep')}
+
+
+@pytest.fixture
+def node_cache_env():
+    old = {k: os.environ.get(k) for k in ('AZ_NODE_CACHE', 'AZ_EMU_SHARP', 'AZ_EMU_VALUE_SCALE')}
+    os.environ['AZ_EMU_SHARP'] = '60'  # peaked stub policy + small values: trees several plies deep, well past the deep build's recorded path
+    os.environ['AZ_EMU_VALUE_SCALE'] = '0.05'
+    yield lambda v: os.environ.__setitem__('AZ_NODE_CACHE', str(v))
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
+def _trajectory(binding, game, n, sims, par, ticks, num_stack=8):
+    A = n * n + (1 if game == 'go' else 0)
+    eng = Engine(game, n, num_games=6, max_simulations=sims, max_parallel=par, net=(1, 16, 16), precision='fp32', seed=21, max_steps=60 if game == 'go' else 0,
+                 num_stack=num_stack, binding=binding)
+    eng.set_weights(_dummy_weights(1, 16, 16, 2 * num_stack + 1, A, n * n if game == 'go' else (n + 4) ** 2))
+    eng.selfplay_begin(sims, par, warm_up_steps=6, check_resign_after_steps=10, resign_threshold=-0.035, disable_resign_ratio=0.5)
+    h = hashlib.sha1()
+    for _ in range(ticks // 10):
+        eng.selfplay_tick(10)
+        games, states, pis, zs = eng.drain_games()
+        for arr in (states, pis, zs, eng.last_moves):
+            h.update(np.ascontiguousarray(arr).tobytes())
+        h.update(repr([sorted(g.items()) for g in games]).encode())
+    for g in range(6):
+        h.update(eng.env_board(g).tobytes())
+        h.update(eng.env_observation(g).tobytes())
+    c = eng.counters()
+    eng.close()
+    assert c['errors'] == 0 and c['games'] > 0
+    return h.hexdigest(), {k: c[k] for k in ('simulations', 'evaluations', 'moves', 'games', 'nodes', 'depth_sum', 'descents', 'samples')}
+
+
+@pytest.mark.parametrize('case', [('go', 9, 96, 4, 8), ('go', 9, 40, 1, 8), ('gomoku', 9, 64, 4, 8), ('go', 5, 64, 8, 3)])
+def test_node_cache_and_deep_paths_give_identical_selfplay(libs, node_cache_env, case):
+    game, n, sims, par, num_stack = case
+    out = {}
+    for variant in ('', 'deep'):
+        for nc in (0, 1):
+            node_cache_env(nc)
+            out[(variant, nc)] = _trajectory(libs[variant], game, n, sims, par, 400, num_stack)
+    base = out[('', 0)]
+    for k, v in out.items():
+        assert v == base, (k, v, base)
+    assert base[1]['depth_sum'] / base[1]['descents'] > 2.2  # mean leaf depth: a good share of the descents passes the deep build's 3 recorded plies
+
+
+@pytest.mark.parametrize('variant,nc', [('', 1), ('deep', 0), ('deep', 1)])
+@pytest.mark.parametrize('game', ['go9', 'gomoku13'])
+def test_reference_traces_in_every_variant(libs, node_cache_env, variant, nc, game):
+    node_cache_env(nc)
+    assert enginecheck.mcts_traces(libs[variant], game) > 50
+    enginecheck.concurrent_searches(libs[variant], game)
