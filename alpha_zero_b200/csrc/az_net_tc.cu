@@ -34,6 +34,10 @@ struct AzNetTc {
   int halo = 0, AR = 0;
   int res_l2 = 0;
   size_t halo_smem = 0;
+  // dense-x kernel (mode 5): 3-D maps [board row][x][channel] of the three activation buffers, tile geometry
+  CUtensorMap xmap_in, xmap_x, xmap_mid;
+  int x_TH = 0, x_sub_bytes = 0, x_sub_stride = 0;
+  size_t x_smem = 0;
   std::vector<CUtensorMap> map_w;
   std::vector<CUtensorMap> map_w_half;  // pair kernel: box of cout/2 weight rows
   std::vector<__nv_bfloat16*> w_dev;
@@ -633,6 +637,299 @@ k_conv_tc_halo(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Dense-x variant (AZ_TC_MODE=5, experimental): the activation rows of a leaf are y*Hc + x with ONE zero board row per leaf
+// and NO separator column (90 rows per 81 positions at 9x9 instead of 100): 10 % fewer MMA rows than the halo kernel.
+// Without a separator column the dx = -1 / +1 taps cannot be row shifts of the same tile (they would wrap around the board
+// edge), so TMA supplies them: the activation matrix is described as a 3-D tensor [board row][x][channel] and the tile is
+// loaded three times with the x coordinate starting at -1, 0, +1 — the out-of-bounds column is filled with zeros by the
+// hardware, which is exactly the padding a 3x3 convolution needs.  The dy taps stay row-shifted UMMA descriptors (+-Hc rows)
+// over each copy.  Sub-tiles (one dx copy of one 64-channel chunk, NBR board rows = TH + 2 Hc rows and change) stream through
+// a 4-slot ring; each feeds 3 taps x 4 K-steps x 2 halves = 24 MMAs.  A tile is TH = floor(256 / Hc) * Hc output rows, so
+// every tile starts on a board-row boundary and both CTAs of a pair use the same descriptor offsets; the 256 - TH surplus
+// rows of the M = 256 MMA are computed and dropped.
+#define X_ASLOTS 4
+#define X_BSTAGES 6
+
+struct XLayer {
+  int cin, cout, relu, has_res;
+  int Hc, RP, guard;
+  int TH;          // output rows per tile (multiple of Hc, <= 256)
+  int sub_bytes;   // bytes of one TMA box = NBR * Hc * 128
+  int sub_stride;  // the same rounded up to 1024 (swizzle atom alignment of the next slot)
+};
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
+template <bool PAIR>
+__global__ void __launch_bounds__(H_THREADS, 1)
+k_conv_tc_x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const float* __restrict__ bias,
+            const __nv_bfloat16* res, __nv_bfloat16* out, const int32_t* __restrict__ n_rows, XLayer L) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int kc = L.cin / TC_BK;
+  const uint32_t b_bytes = (uint32_t)(PAIR ? L.cout / 2 : L.cout) * TC_BK * 2;  // a pair splits every weight chunk along N
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  const int cw = L.cout / 2;                 // columns per epilogue warp, processed 32 at a time
+  const uint32_t srow = 32 * 2 + 16;         // staging row pitch (bytes)
+  unsigned char* smA = smem;
+  unsigned char* smB = smem + (size_t)X_ASLOTS * L.sub_stride;
+  unsigned char* smS = smB + (size_t)X_BSTAGES * b_bytes;
+  float* s_bias = (float*)(smS + (size_t)H_EPI_WARPS * 32 * srow);
+  uint64_t* a_full = (uint64_t*)(s_bias + L.cout);
+  uint64_t* a_empty = a_full + X_ASLOTS;
+  uint64_t* b_full = a_empty + X_ASLOTS;
+  uint64_t* b_empty = b_full + X_BSTAGES;
+  uint64_t* tfull_bar = b_empty + X_BSTAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long M = (long long)(*n_rows) * L.RP;
+  const int num_tiles = (int)((M + L.TH - 1) / L.TH);
+  const int num_units = PAIR ? (num_tiles + 1) / 2 : num_tiles;
+  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int ustep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  uint32_t tmem_cols = 4 * (uint32_t)L.cout;  // 2 halves x 2 accumulator stages
+  tmem_cols = tmem_cols <= 32 ? 32 : tmem_cols <= 64 ? 64 : tmem_cols <= 128 ? 128 : tmem_cols <= 256 ? 256 : 512;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < X_ASLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], H_MMA_WARPS); }
+    for (int s = 0; s < X_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], H_MMA_WARPS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], H_MMA_WARPS); mbar_init(&tempty_bar[s], PAIR ? 2 * H_EPI_WARPS : H_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int c = threadIdx.x; c < L.cout; c += blockDim.x) s_bias[c] = bias[c];
+  if (warp == 1) {
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: sub-tiles (kk, dx) and weight chunks (kk, dx, dy) in the order the MMA warps consume them =====
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+      int bstage = 0;
+      uint32_t bphase = 0, ai = 0;
+      for (int u = unit0; u < num_units; u += ustep) {
+        const int tt = PAIR ? 2 * u + (int)crank : u;
+        const int br0 = (L.guard + tt * L.TH) / L.Hc - 1;  // first board row of the box: one above the tile
+        for (int kk = 0; kk < kc; ++kk) {
+          for (int dxi = 0; dxi < 3; ++dxi, ++ai) {
+            const uint32_t slot = ai % X_ASLOTS, par = (ai / X_ASLOTS) & 1u;
+            mbar_wait(&a_empty[slot], par ^ 1u);
+            unsigned char* dst = smA + (size_t)slot * L.sub_stride;
+            if (PAIR) {
+              if (crank == 0) mbar_expect_tx(&a_full[slot], 2u * (uint32_t)L.sub_bytes);
+              tma_load_3d_pair(dst, &map_a, &a_full[slot], kk * TC_BK, dxi - 1, br0);
+            } else {
+              mbar_expect_tx(&a_full[slot], (uint32_t)L.sub_bytes);
+              tma_load_3d(dst, &map_a, &a_full[slot], kk * TC_BK, dxi - 1, br0);
+            }
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              const int tap = dyi * 3 + dxi;
+              mbar_wait(&b_empty[bstage], bphase ^ 1);
+              if (PAIR) {
+                if (crank == 0) mbar_expect_tx(&b_full[bstage], 2 * b_bytes);
+                tma_load_2d_pair(smB + (size_t)bstage * b_bytes, &map_b, &b_full[bstage], kk * TC_BK, tap * L.cout + (int)crank * (L.cout / 2));
+              } else {
+                mbar_expect_tx(&b_full[bstage], b_bytes);
+                tma_load_2d(smB + (size_t)bstage * b_bytes, &map_b, &b_full[bstage], kk * TC_BK, tap * L.cout);
+              }
+              if (++bstage == X_BSTAGES) { bstage = 0; bphase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp <= H_MMA_WARPS) {
+   if (!PAIR || crank == 0) {
+    // ===== MMA issuers: warp 1 owns rows 0..127 of the tile, warp 2 rows 128..255 =================================
+    const int h = warp - 1;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(L.cout >> 3) << 17) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
+    const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO | version 1 | SWIZZLE_128B  (bits 32..63)
+    uint32_t b_lo[X_BSTAGES];
+#pragma unroll
+    for (int s2 = 0; s2 < X_BSTAGES; ++s2) b_lo[s2] = ((smem_u32(smB + (size_t)s2 * b_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+    // output row 0 of the tile is row Hc of every box (the box starts one board row above); (>>4) units: 8 per 128-byte row
+    const uint32_t row0_16 = (uint32_t)(L.Hc + h * 128) * 8u;
+    const bool leader = elect_one();
+    int bstage = 0, it = 0;
+    uint32_t bphase = 0, ai = 0;
+    for (int u = unit0; u < num_units; u += ustep, ++it) {
+      const int acc = it & 1;
+      mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)((acc * 2 + h) * L.cout);
+      for (int kk = 0; kk < kc; ++kk) {
+        for (int dxi = 0; dxi < 3; ++dxi, ++ai) {
+          const uint32_t slot = ai % X_ASLOTS, par = (ai / X_ASLOTS) & 1u;
+          mbar_wait(&a_full[slot], par);
+          tc_fence_after();
+          const uint32_t a_lo0 = (((smem_u32(smA + (size_t)slot * L.sub_stride) & 0x3FFFFu) >> 4) + row0_16) | (1u << 16);
+          for (int dyi = 0; dyi < 3; ++dyi) {
+            mbar_wait(&b_full[bstage], bphase);
+            tc_fence_after();
+            if (leader) {
+              const uint32_t alo = (uint32_t)((int)a_lo0 + (dyi - 1) * L.Hc * 8);
+              const uint32_t blo = b_lo[bstage];
+#pragma unroll
+              for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
+                const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(alo + (uint32_t)k4 * 2u);
+                const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(blo + (uint32_t)k4 * 2u);
+                const uint32_t accum = (kk | dxi | dyi | k4) != 0 ? 1u : 0u;
+                if (PAIR) tc_mma_pair(d_tmem, ad, bd, idesc, accum);
+                else tc_mma(d_tmem, ad, bd, idesc, accum);
+              }
+              if (PAIR) tc_commit_pair(&b_empty[bstage]);
+              else tc_commit(&b_empty[bstage]);
+            }
+            __syncwarp();
+            if (++bstage == X_BSTAGES) { bstage = 0; bphase ^= 1; }
+          }
+          if (leader) {
+            if (PAIR) tc_commit_pair(&a_empty[slot]);
+            else tc_commit(&a_empty[slot]);
+          }
+          __syncwarp();
+        }
+      }
+      if (leader) {
+        if (PAIR) tc_commit_pair(&tfull_bar[acc]);
+        else tc_commit(&tfull_bar[acc]);
+      }
+      __syncwarp();
+    }
+   }
+  } else {
+    // ===== epilogue: as in k_conv_tc_halo; rows >= TH of the M = 256 tile belong to the next tile and are dropped =====
+    const int ew = warp - (1 + H_MMA_WARPS);  // 0..7
+    const int q = warp & 3;                   // TMEM lane quarter this warp may read
+    const int ch = ew >> 2;                   // column half
+    const int col0 = ch * cw;
+    const int npass_c = cw / 32;
+    unsigned char* stage = smS + (size_t)ew * 32 * srow;
+    const int crow = lane >> 2, cchunk = lane & 3;
+    uint4 pre[4];
+    // rows of a pass: tile row l0 + i*8 + crow (coalesced phases) / l0 + lane (TMEM phase)
+    auto prefetch = [&](long long tile_row0, int l0, int cc) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int l = l0 + i * 8 + crow;
+        const long long mr = tile_row0 + l;
+        pre[i] = make_uint4(0, 0, 0, 0);
+        if (l < L.TH && mr < M) pre[i] = *reinterpret_cast<const uint4*>(res + ((size_t)L.guard + (size_t)mr) * L.cout + cc + cchunk * 8);
+      }
+    };
+    int it = 0;
+    const int tstep = PAIR ? 2 * ustep : ustep;
+    const int t_first = PAIR ? 2 * unit0 + (int)crank : unit0;
+    if (L.has_res && unit0 < num_units) prefetch((long long)t_first * L.TH, q * 32, col0);
+    for (int u = unit0; u < num_units; u += ustep, ++it) {
+      const int t = PAIR ? 2 * u + (int)crank : u;
+      const long long tile_row0 = (long long)t * L.TH;
+      const int acc = it & 1;
+      mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ps = 0; ps < 2 * npass_c; ++ps) {
+        const int h = ps / npass_c, pc = ps - h * npass_c;
+        const int cc = col0 + pc * 32;
+        const int l0 = h * 128 + q * 32;
+        uint32_t v[32];
+        tc_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * 2 + h) * L.cout + cc), v);
+        if (L.has_res) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stage + (size_t)(i * 8 + crow) * srow + cchunk * 16) = pre[i];
+          const int nps = ps + 1;
+          if (nps < 2 * npass_c) {
+            const int nh = nps / npass_c, npc = nps - nh * npass_c;
+            prefetch(tile_row0, nh * 128 + q * 32, col0 + npc * 32);
+          } else if (u + ustep < num_units) {
+            prefetch((long long)(t + tstep) * L.TH, q * 32, col0);
+          }
+        }
+        __syncwarp();
+        const int l = l0 + lane;
+        const long long m = tile_row0 + l;
+        const int r = (int)(m % L.RP);
+        const bool valid = (l < L.TH) && (m < M) && (r / L.Hc) < L.Hc;  // the leaf's last board row is its zero row
+        unsigned char* myrow = stage + (size_t)lane * srow;
+        {
+          tc_wait_ld();
+          __align__(16) __nv_bfloat16 o[32];
+          if (valid) {
+            __align__(16) __nv_bfloat16 rr[32];
+            if (L.has_res) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) reinterpret_cast<uint4*>(rr)[k] = *reinterpret_cast<const uint4*>(myrow + k * 16);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float f = __uint_as_float(v[j]) + s_bias[cc + j];
+              if (L.has_res) f += __bfloat162float(rr[j]);
+              if (L.relu) f = fmaxf(f, 0.f);
+              o[j] = __float2bfloat16(f);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __float2bfloat16(0.f);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(myrow + k * 16) = reinterpret_cast<const uint4*>(o)[k];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ls = l0 + i * 8 + crow;
+          const long long mr = tile_row0 + ls;
+          if (ls < L.TH && mr < M)
+            *reinterpret_cast<uint4*>(out + ((size_t)L.guard + (size_t)mr) * L.cout + cc + cchunk * 8) =
+                *reinterpret_cast<const uint4*>(stage + (size_t)(i * 8 + crow) * srow + cchunk * 16);
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR && crank != 0) mbar_arrive_remote(&tempty_bar[acc], 0);
+        else mbar_arrive(&tempty_bar[acc]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -662,6 +959,19 @@ static int make_map(CUtensorMap* m, void* base, uint64_t inner, uint64_t rows, u
   return 0;
 }
 
+static int make_map_3d(CUtensorMap* m, void* base, uint64_t inner, uint64_t width, uint64_t board_rows, uint32_t box_rows, std::string& err) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { err = "cuTensorMapEncodeTiled not available"; return AZ_ERR_CUDA; }
+  cuuint64_t dims[3] = {inner, width, board_rows};
+  cuuint64_t strides[2] = {inner * 2, inner * 2 * width};
+  cuuint32_t box[3] = {TC_BK, (cuuint32_t)width, box_rows};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled (3-D) failed with code " + std::to_string((int)r); return AZ_ERR_CUDA; }
+  return 0;
+}
+
 int aznet_tc_create(AzNet* n, AzRt& rt, std::string& err) {
   AzNetTc* tc = new AzNetTc();
   n->tc = tc;
@@ -686,6 +996,30 @@ int aznet_tc_create(AzNet* n, AzRt& rt, std::string& err) {
   const char* md = getenv("AZ_TC_MODE");
   tc->mode = md ? atoi(md) : 4;  // 4 = halo tile + 2-CTA pairs (default), 2 = halo tile single CTA, 0 = one TMA box per tap
   if (n->C > 128) tc->mode = 0;  // the halo tile of a 256-channel layer does not fit next to the weight ring
+  if (tc->mode == 5 || tc->mode == 6) {
+    // dense-x layout (experimental, opt-in): rows y*Hc + x, one zero board row per leaf, no separator column.  The input and
+    // head kernels follow NetGeom, so only the geometry changes for them.  6 = the single-CTA build of the same kernel.
+    NetGeom& g = n->g;
+    g.Wr = g.Hc;
+    g.RP = g.Hc * (g.Hc + 1);
+    g.guard = g.Hc * 16;  // a whole number of board rows, so that board rows of the 3-D view start at matrix row 0
+    tc->x_TH = 256 / g.Hc * g.Hc;
+    const int nbr = (256 + 2 * g.Hc + g.Hc - 1) / g.Hc;
+    tc->x_sub_bytes = nbr * g.Hc * 128;
+    tc->x_sub_stride = (tc->x_sub_bytes + 1023) / 1024 * 1024;
+    const uint64_t board_rows = n->rows_total / (uint64_t)g.Hc;
+    rc = make_map_3d(&tc->xmap_in, n->act_in, 64, g.Hc, board_rows, nbr, err);
+    if (!rc) rc = make_map_3d(&tc->xmap_x, n->act_x, n->C, g.Hc, board_rows, nbr, err);
+    if (!rc) rc = make_map_3d(&tc->xmap_mid, n->act_mid, n->C, g.Hc, board_rows, nbr, err);
+    if (rc) return rc;
+    tc->x_smem = (size_t)X_ASLOTS * tc->x_sub_stride + (size_t)X_BSTAGES * n->C * TC_BK * 2 + (size_t)H_EPI_WARPS * 32 * 80 + (size_t)n->C * 4 +
+                 (size_t)(2 * X_ASLOTS + 2 * X_BSTAGES + 4) * 8 + 16 + 1024;
+    if (tc->x_smem > 227 * 1024) { err = "dense-x conv kernel: tile does not fit in shared memory for this board size"; return AZ_ERR_CAPACITY; }
+    e = cudaFuncSetAttribute(k_conv_tc_x<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc->x_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_tc_x<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc->x_smem);
+    if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute(dense-x): ") + cudaGetErrorString(e); return AZ_ERR_CUDA; }
+    return 0;
+  }
   if (tc->mode) {
     tc->halo = n->g.Wr + 1;
     tc->AR = (256 + 2 * tc->halo + 7) / 8 * 8;
@@ -771,6 +1105,48 @@ int aznet_tc_forward(AzNet* n, AzRt& rt, const int8_t* obs_base, const int32_t* 
     rt.launches++;
   }
   const long long Mmax = (long long)max_rows * g.RP;
+  if (tc->mode == 5 || tc->mode == 6) {
+    const bool pair = tc->mode == 5;
+    const long long tiles = (Mmax + tc->x_TH - 1) / tc->x_TH;
+    const int xgrid = pair ? (int)std::max<long long>(2, std::min<long long>((tiles + 1) / 2 * 2, tc->num_sms & ~1))
+                           : (int)std::max<long long>(1, std::min<long long>(tiles, tc->num_sms));
+    XLayer X5;
+    X5.Hc = g.Hc; X5.RP = g.RP; X5.guard = g.guard; X5.TH = tc->x_TH; X5.sub_bytes = tc->x_sub_bytes; X5.sub_stride = tc->x_sub_stride;
+    __nv_bfloat16* X = (__nv_bfloat16*)n->act_x;
+    __nv_bfloat16* MID = (__nv_bfloat16*)n->act_mid;
+    auto launch = [&](const CUtensorMap& ma, int wi, const float* bias, const __nv_bfloat16* resp, __nv_bfloat16* outp) {
+      if (!pair) {
+        k_conv_tc_x<false><<<xgrid, H_THREADS, tc->x_smem, rt.stream>>>(ma, tc->map_w[wi], bias, resp, outp, n_rows_dev, X5);
+      } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)xgrid);
+        cfg.blockDim = dim3(H_THREADS);
+        cfg.dynamicSmemBytes = tc->x_smem;
+        cfg.stream = rt.stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, k_conv_tc_x<true>, ma, tc->map_w_half[wi], bias, resp, outp, n_rows_dev, X5);
+      }
+      rt.launches++;
+    };
+    X5.cin = 64; X5.cout = n->C; X5.relu = 1; X5.has_res = 0;
+    launch(tc->xmap_in, 0, n->conv_b[0], nullptr, X);
+    X5.cin = n->C;
+    for (int b = 0; b < n->blocks; ++b) {
+      X5.has_res = 0;
+      launch(tc->xmap_x, 1 + 2 * b, n->conv_b[1 + 2 * b], nullptr, MID);
+      X5.has_res = 1;
+      launch(tc->xmap_mid, 2 + 2 * b, n->conv_b[2 + 2 * b], X, X);
+    }
+    launch_heads<__nv_bfloat16>(rt.stream, X, row_list, n_rows_dev, n->hp, g, n->C, n->A, n->fc, priors_base, values_base, pri_stride, max_rows);
+    rt.launches++;
+    cudaError_t xe = cudaGetLastError();
+    if (xe != cudaSuccess) { g_az_error = std::string("tensor-core tower (dense-x) launch: ") + cudaGetErrorString(xe); return AZ_ERR_CUDA; }
+    return AZ_OK;
+  }
   if (tc->mode) {
     const int hgrid = (int)std::max<long long>(2, std::min<long long>((Mmax + 255) / 256, tc->num_sms));
     HaloLayer H;
