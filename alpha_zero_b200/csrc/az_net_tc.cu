@@ -658,6 +658,7 @@ struct XLayer {
   int TH;          // output rows per tile (multiple of Hc, <= 256)
   int sub_bytes;   // bytes of one TMA box = NBR * Hc * 128
   int sub_stride;  // the same rounded up to 1024 (swizzle atom alignment of the next slot)
+  int bstages;     // weight ring depth: X_BSTAGES for a pair (half chunks), half of it for a single CTA (same bytes)
 };
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
@@ -686,7 +687,7 @@ k_conv_tc_x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   const uint32_t srow = 32 * 2 + 16;         // staging row pitch (bytes)
   unsigned char* smA = smem;
   unsigned char* smB = smem + (size_t)X_ASLOTS * L.sub_stride;
-  unsigned char* smS = smB + (size_t)X_BSTAGES * b_bytes;
+  unsigned char* smS = smB + (size_t)L.bstages * b_bytes;
   float* s_bias = (float*)(smS + (size_t)H_EPI_WARPS * 32 * srow);
   uint64_t* a_full = (uint64_t*)(s_bias + L.cout);
   uint64_t* a_empty = a_full + X_ASLOTS;
@@ -707,7 +708,7 @@ k_conv_tc_x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < X_ASLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], H_MMA_WARPS); }
-    for (int s = 0; s < X_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], H_MMA_WARPS); }
+    for (int s = 0; s < L.bstages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], H_MMA_WARPS); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], H_MMA_WARPS); mbar_init(&tempty_bar[s], PAIR ? 2 * H_EPI_WARPS : H_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -759,7 +760,7 @@ k_conv_tc_x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 mbar_expect_tx(&b_full[bstage], b_bytes);
                 tma_load_2d(smB + (size_t)bstage * b_bytes, &map_b, &b_full[bstage], kk * TC_BK, tap * L.cout);
               }
-              if (++bstage == X_BSTAGES) { bstage = 0; bphase ^= 1; }
+              if (++bstage == L.bstages) { bstage = 0; bphase ^= 1; }
             }
           }
         }
@@ -808,7 +809,7 @@ k_conv_tc_x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
               else tc_commit(&b_empty[bstage]);
             }
             __syncwarp();
-            if (++bstage == X_BSTAGES) { bstage = 0; bphase ^= 1; }
+            if (++bstage == L.bstages) { bstage = 0; bphase ^= 1; }
           }
           if (leader) {
             if (PAIR) tc_commit_pair(&a_empty[slot]);
@@ -1012,7 +1013,8 @@ int aznet_tc_create(AzNet* n, AzRt& rt, std::string& err) {
     if (!rc) rc = make_map_3d(&tc->xmap_x, n->act_x, n->C, g.Hc, board_rows, nbr, err);
     if (!rc) rc = make_map_3d(&tc->xmap_mid, n->act_mid, n->C, g.Hc, board_rows, nbr, err);
     if (rc) return rc;
-    tc->x_smem = (size_t)X_ASLOTS * tc->x_sub_stride + (size_t)X_BSTAGES * n->C * TC_BK * 2 + (size_t)H_EPI_WARPS * 32 * 80 + (size_t)n->C * 4 +
+    // weight ring: X_BSTAGES half chunks per CTA of a pair == X_BSTAGES / 2 whole chunks for a single CTA
+    tc->x_smem = (size_t)X_ASLOTS * tc->x_sub_stride + (size_t)X_BSTAGES * (n->C / 2) * TC_BK * 2 + (size_t)H_EPI_WARPS * 32 * 80 + (size_t)n->C * 4 +
                  (size_t)(2 * X_ASLOTS + 2 * X_BSTAGES + 4) * 8 + 16 + 1024;
     if (tc->x_smem > 227 * 1024) { err = "dense-x conv kernel: tile does not fit in shared memory for this board size"; return AZ_ERR_CAPACITY; }
     e = cudaFuncSetAttribute(k_conv_tc_x<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc->x_smem);
@@ -1111,7 +1113,7 @@ int aznet_tc_forward(AzNet* n, AzRt& rt, const int8_t* obs_base, const int32_t* 
     const int xgrid = pair ? (int)std::max<long long>(2, std::min<long long>((tiles + 1) / 2 * 2, tc->num_sms & ~1))
                            : (int)std::max<long long>(1, std::min<long long>(tiles, tc->num_sms));
     XLayer X5;
-    X5.Hc = g.Hc; X5.RP = g.RP; X5.guard = g.guard; X5.TH = tc->x_TH; X5.sub_bytes = tc->x_sub_bytes; X5.sub_stride = tc->x_sub_stride;
+    X5.Hc = g.Hc; X5.RP = g.RP; X5.guard = g.guard; X5.TH = tc->x_TH; X5.sub_bytes = tc->x_sub_bytes; X5.sub_stride = tc->x_sub_stride; X5.bstages = pair ? X_BSTAGES : X_BSTAGES / 2;
     __nv_bfloat16* X = (__nv_bfloat16*)n->act_x;
     __nv_bfloat16* MID = (__nv_bfloat16*)n->act_mid;
     auto launch = [&](const CUtensorMap& ma, int wi, const float* bias, const __nv_bfloat16* resp, __nv_bfloat16* outp) {
