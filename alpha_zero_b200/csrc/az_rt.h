@@ -62,7 +62,11 @@ static inline void rt_destroy(AzRt& rt) {
 static inline void* rt_alloc(size_t bytes) {
   void* p = nullptr;
   if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+  // cudaMemset on device memory is asynchronous and runs on the legacy default stream, which the engine's non-blocking
+  // stream does not wait for: without this synchronisation the zero fill can land AFTER the first copy / kernel that
+  // uses the buffer (seen when several processes share the GPU: freshly uploaded weights came back as zeros)
   cudaMemset(p, 0, bytes ? bytes : 1);
+  cudaStreamSynchronize(0);
   return p;
 }
 static inline void rt_free(void* p) { if (p) cudaFree(p); }

@@ -635,6 +635,14 @@ AZ_DEV int game_commit(const AzState& E, int g, int move, double* best_child_q) 
     for (int i = 0; i < count; ++i) {
       const int old = remap[i];
       int base = count;
+      if (i + 3 < count) {  // the breadth-first queue is ahead of us: start fetching the rows of a node we will copy soon
+        const size_t pf = (size_t)remap[i + 3];
+        w_prefetch(To.N + pf * Ap, Ap * 4);
+        w_prefetch(To.W + pf * Ap, Ap * 4);
+        w_prefetch(To.P + pf * Ap, Ap * 4);
+        w_prefetch(To.cidx + pf * Ap, Ap * 2);
+        if (To.nboard) { w_prefetch(To.nboard + pf * d.ncp, d.ncp); w_prefetch(To.nlegal + pf * Ap, Ap); }
+      }
       for (int a0 = 0; a0 < Ap; a0 += AZ_WIDTH) {
         const int a = a0 + AZ_LANE;
         Tn.N[(size_t)i * Ap + a] = To.N[(size_t)old * Ap + a];
@@ -790,15 +798,20 @@ AZ_DEV void game_advance(const AzState& E, int g, Sim& S) {
   }
   w_sync();
   head = (unsigned long long)E.res_q[(size_t)g * 2 + 1];
-  for (int i = 0; i < len; ++i) {
-    const size_t slot = (size_t)((head + i) % (unsigned long long)d.ring_cap);
-    const int8_t* so = E.g_obs + ((size_t)g * d.max_len + i) * d.obs_bytes;
-    int8_t* dob = E.r_obs + slot * d.obs_bytes;
-    W_FOR(k, d.obs_bytes) dob[k] = so[k];
-    const float* sp = E.g_pi + ((size_t)g * d.max_len + i) * d.A;
-    float* dp = E.r_pi + slot * d.A;
-    W_FOR(a, d.A) dp[a] = sp[a];
-    W_LANE0 {
+  {
+    // the samples of one game are contiguous in the record and in the ring (modulo wrap): at most two flat copies per array
+    const size_t s0 = (size_t)(head % (unsigned long long)d.ring_cap);
+    const size_t n1 = (size_t)len < (size_t)d.ring_cap - s0 ? (size_t)len : (size_t)d.ring_cap - s0, n2 = (size_t)len - n1;
+    const int8_t* so = E.g_obs + (size_t)g * d.max_len * d.obs_bytes;
+    const float* sp = E.g_pi + (size_t)g * d.max_len * d.A;
+    w_copy_bytes(E.r_obs + s0 * d.obs_bytes, so, n1 * d.obs_bytes);
+    w_copy_words(E.r_pi + s0 * d.A, sp, n1 * d.A);
+    if (n2) {
+      w_copy_bytes(E.r_obs, so + n1 * d.obs_bytes, n2 * d.obs_bytes);
+      w_copy_words(E.r_pi, sp + n1 * d.A, n2 * d.A);
+    }
+    W_FOR(i, len) {
+      const size_t slot = (size_t)((head + i) % (unsigned long long)d.ring_cap);
       float z = 0.f;
       if (reward != 0.f) z = (E.g_to_play[(size_t)g * d.max_len + i] == last_player) ? reward : -reward;
       E.r_z[slot] = z;

@@ -95,6 +95,77 @@ AZ_DEV unsigned long long atomic_add_u64(unsigned long long* p, unsigned long lo
 #define W_FOR(i, n) for (int i = AZ_LANE; i < (n); i += AZ_WIDTH)
 #define W_LANE0 if (AZ_LANE == 0)
 
+// Hint: pull the 128-byte lines of [p, p + bytes) towards L2 (one line per lane); results never depend on it.
+AZ_DEV void w_prefetch(const void* p, int bytes) {
+#ifndef AZ_EMU
+  const int off = AZ_LANE * 128;
+  if (off < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)p + off));
+#else
+  (void)p; (void)bytes;
+#endif
+}
+
+// Warp-cooperative copy of n bytes between global buffers of ANY alignment (finished games: per-slot record -> sample ring).
+// Destination words are written whole; each is assembled from the two aligned source words it straddles (funnel shift), four
+// words per lane in flight.  The last source word read may extend up to 3 bytes past src + n: inside the allocation, whose size
+// cudaMalloc rounds up to 256 bytes.
+AZ_DEV void w_copy_bytes(void* dst_, const void* src_, size_t n) {
+#ifdef AZ_EMU
+  memmove(dst_, src_, n);
+#else
+  unsigned char* dst = (unsigned char*)dst_;
+  const unsigned char* src = (const unsigned char*)src_;
+  size_t head = (4 - ((size_t)dst & 3)) & 3;
+  if (head > n) head = n;
+  if ((size_t)AZ_LANE < head) dst[AZ_LANE] = src[AZ_LANE];
+  uint32_t* d4 = (uint32_t*)(dst + head);
+  const unsigned char* s = src + head;
+  const size_t nw = (n - head) >> 2;
+  const uint32_t r = (uint32_t)((size_t)s & 3);
+  const uint32_t* sa = (const uint32_t*)(s - r);
+  const uint32_t sh = r * 8;
+  for (size_t j0 = 0; j0 < nw; j0 += 4 * AZ_WIDTH) {
+    uint32_t lo[4], hi[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const size_t j = j0 + (size_t)k * AZ_WIDTH + AZ_LANE;
+      lo[k] = 0; hi[k] = 0;
+      if (j < nw) { lo[k] = sa[j]; if (r) hi[k] = sa[j + 1]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const size_t j = j0 + (size_t)k * AZ_WIDTH + AZ_LANE;
+      if (j < nw) d4[j] = r ? __funnelshift_r(lo[k], hi[k], sh) : lo[k];
+    }
+  }
+  const size_t done = head + nw * 4;
+  if ((size_t)AZ_LANE < n - done) dst[done + AZ_LANE] = src[done + AZ_LANE];
+#endif
+}
+
+// Same for 4-byte elements (both sides 4-byte aligned).
+AZ_DEV void w_copy_words(void* dst_, const void* src_, size_t nwords) {
+#ifdef AZ_EMU
+  memmove(dst_, src_, nwords * 4);
+#else
+  uint32_t* d4 = (uint32_t*)dst_;
+  const uint32_t* s4 = (const uint32_t*)src_;
+  for (size_t j0 = 0; j0 < nwords; j0 += 4 * AZ_WIDTH) {
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const size_t j = j0 + (size_t)k * AZ_WIDTH + AZ_LANE;
+      v[k] = j < nwords ? s4[j] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const size_t j = j0 + (size_t)k * AZ_WIDTH + AZ_LANE;
+      if (j < nwords) d4[j] = v[k];
+    }
+  }
+#endif
+}
+
 // Counter-based RNG (SplitMix64 finaliser over (seed, stream, counter)): stateless, identical on
 // every lane, so a warp can draw element-wise without communication.
 AZ_DEV uint64_t az_mix64(uint64_t z) {
