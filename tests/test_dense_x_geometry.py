@@ -18,7 +18,7 @@ def _tma_box(act3, c0, x0, br0, nbr, hc):
     return box.reshape(nbr * hc, 64)  # shared-memory rows, 128 bytes each
 
 
-@pytest.mark.parametrize('hc,leaves,cin', [(9, 7, 64), (9, 3, 128), (17, 2, 64), (5, 11, 64)])
+@pytest.mark.parametrize('hc,leaves,cin', [(9, 7, 64), (9, 3, 128), (17, 2, 64), (5, 11, 64), (13, 4, 64), (19, 3, 64)])
 def test_dense_x_equals_zero_padded_conv(hc, leaves, cin):
     rng = np.random.default_rng(hc * 100 + leaves)
     cout = 8
