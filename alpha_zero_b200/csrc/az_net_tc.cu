@@ -22,6 +22,9 @@
 #include "az_net_impl.h"
 #include "az_net_kernels.cuh"
 
+#ifndef AZ_TC_MODE_DEFAULT
+#define AZ_TC_MODE_DEFAULT 5
+#endif
 #define TC_STAGES 4
 #define TC_BM 128
 #define TC_BK 64
@@ -639,7 +642,7 @@ k_conv_tc_halo(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 
 
 // ---------------------------------------------------------------------------------------------------
-// Dense-x variant (AZ_TC_MODE=5, experimental): the activation rows of a leaf are y*Hc + x with ONE zero board row per leaf
+// Dense-x variant (AZ_TC_MODE=5, the default for <= 128 filters): the activation rows of a leaf are y*Hc + x with ONE zero board row per leaf
 // and NO separator column (90 rows per 81 positions at 9x9 instead of 100): 10 % fewer MMA rows than the halo kernel.
 // Without a separator column the dx = -1 / +1 taps cannot be row shifts of the same tile (they would wrap around the board
 // edge), so TMA supplies them: the activation matrix is described as a 3-D tensor [board row][x][channel] and the tile is
@@ -995,32 +998,41 @@ int aznet_tc_create(AzNet* n, AzRt& rt, std::string& err) {
   const char* rp = getenv("AZ_TC_RESPF");
   tc->res_l2 = rp ? atoi(rp) : 0;
   const char* md = getenv("AZ_TC_MODE");
-  tc->mode = md ? atoi(md) : 4;  // 4 = halo tile + 2-CTA pairs (default), 2 = halo tile single CTA, 0 = one TMA box per tap
+  // 5 = dense-x layout + 2-CTA pairs (default), 6 = dense-x single CTA, 4 = halo tile + 2-CTA pairs, 2 = halo tile single CTA,
+  // 0 = one TMA box per tap
+  tc->mode = md ? atoi(md) : AZ_TC_MODE_DEFAULT;
   if (n->C > 128) tc->mode = 0;  // the halo tile of a 256-channel layer does not fit next to the weight ring
   if (tc->mode == 5 || tc->mode == 6) {
-    // dense-x layout (experimental, opt-in): rows y*Hc + x, one zero board row per leaf, no separator column.  The input and
-    // head kernels follow NetGeom, so only the geometry changes for them.  6 = the single-CTA build of the same kernel.
-    NetGeom& g = n->g;
-    g.Wr = g.Hc;
-    g.RP = g.Hc * (g.Hc + 1);
-    g.guard = g.Hc * 16;  // a whole number of board rows, so that board rows of the 3-D view start at matrix row 0
-    tc->x_TH = 256 / g.Hc * g.Hc;
-    const int nbr = (256 + 2 * g.Hc + g.Hc - 1) / g.Hc;
-    tc->x_sub_bytes = nbr * g.Hc * 128;
-    tc->x_sub_stride = (tc->x_sub_bytes + 1023) / 1024 * 1024;
-    const uint64_t board_rows = n->rows_total / (uint64_t)g.Hc;
-    rc = make_map_3d(&tc->xmap_in, n->act_in, 64, g.Hc, board_rows, nbr, err);
-    if (!rc) rc = make_map_3d(&tc->xmap_x, n->act_x, n->C, g.Hc, board_rows, nbr, err);
-    if (!rc) rc = make_map_3d(&tc->xmap_mid, n->act_mid, n->C, g.Hc, board_rows, nbr, err);
-    if (rc) return rc;
+    // dense-x layout: rows y*Hc + x, one zero board row per leaf, no separator column.  The input and head kernels follow
+    // NetGeom, so only the geometry changes for them.  6 = the single-CTA build of the same kernel.  A canvas too wide for the
+    // shared-memory ring (Hc > 19 with 128 filters) keeps the halo kernel.
+    const int Hc = n->g.Hc;
+    const int nbr = (256 + 2 * Hc + Hc - 1) / Hc;
+    const int sub_bytes = nbr * Hc * 128, sub_stride = (sub_bytes + 1023) / 1024 * 1024;
     // weight ring: X_BSTAGES half chunks per CTA of a pair == X_BSTAGES / 2 whole chunks for a single CTA
-    tc->x_smem = (size_t)X_ASLOTS * tc->x_sub_stride + (size_t)X_BSTAGES * (n->C / 2) * TC_BK * 2 + (size_t)H_EPI_WARPS * 32 * 80 + (size_t)n->C * 4 +
-                 (size_t)(2 * X_ASLOTS + 2 * X_BSTAGES + 4) * 8 + 16 + 1024;
-    if (tc->x_smem > 227 * 1024) { err = "dense-x conv kernel: tile does not fit in shared memory for this board size"; return AZ_ERR_CAPACITY; }
-    e = cudaFuncSetAttribute(k_conv_tc_x<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc->x_smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_tc_x<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc->x_smem);
-    if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute(dense-x): ") + cudaGetErrorString(e); return AZ_ERR_CUDA; }
-    return 0;
+    const size_t x_smem = (size_t)X_ASLOTS * sub_stride + (size_t)X_BSTAGES * (n->C / 2) * TC_BK * 2 + (size_t)H_EPI_WARPS * 32 * 80 + (size_t)n->C * 4 +
+                          (size_t)(2 * X_ASLOTS + 2 * X_BSTAGES + 4) * 8 + 16 + 1024;
+    if (x_smem > 227 * 1024) {
+      tc->mode = 4;
+    } else {
+      NetGeom& g = n->g;
+      g.Wr = Hc;
+      g.RP = Hc * (Hc + 1);
+      g.guard = Hc * 16;  // a whole number of board rows, so that board rows of the 3-D view start at matrix row 0
+      tc->x_TH = 256 / Hc * Hc;
+      tc->x_sub_bytes = sub_bytes;
+      tc->x_sub_stride = sub_stride;
+      tc->x_smem = x_smem;
+      const uint64_t board_rows = n->rows_total / (uint64_t)Hc;
+      rc = make_map_3d(&tc->xmap_in, n->act_in, 64, Hc, board_rows, nbr, err);
+      if (!rc) rc = make_map_3d(&tc->xmap_x, n->act_x, n->C, Hc, board_rows, nbr, err);
+      if (!rc) rc = make_map_3d(&tc->xmap_mid, n->act_mid, n->C, Hc, board_rows, nbr, err);
+      if (rc) return rc;
+      e = cudaFuncSetAttribute(k_conv_tc_x<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc->x_smem);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_tc_x<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc->x_smem);
+      if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute(dense-x): ") + cudaGetErrorString(e); return AZ_ERR_CUDA; }
+      return 0;
+    }
   }
   if (tc->mode) {
     tc->halo = n->g.Wr + 1;

@@ -632,44 +632,93 @@ AZ_DEV int game_commit(const AzState& E, int g, int move, double* best_child_q) 
     W_LANE0 remap[0] = (int16_t)child;
     w_sync();
     int count = 1;
+    constexpr int KC = 3;  // chunks of AZ_WIDTH entries fetched together: one round of loads per node at 9x9 (Ap = 96)
+    // ---- pass 1, structure: breadth-first numbering.  Only the link rows are read; a node's links are all requested before the
+    //      first one is consumed, and the links of a node further down the queue are prefetched, so the dependent chain per
+    //      node is one (mostly L2) round trip instead of one per 32 actions.
     for (int i = 0; i < count; ++i) {
       const int old = remap[i];
+      if (i + 4 < count) w_prefetch(To.cidx + (size_t)remap[i + 4] * Ap, Ap * 2);
       int base = count;
-      if (i + 3 < count) {  // the breadth-first queue is ahead of us: start fetching the rows of a node we will copy soon
-        const size_t pf = (size_t)remap[i + 3];
+      for (int a00 = 0; a00 < Ap; a00 += KC * AZ_WIDTH) {
+        int c[KC];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+          const int a = a00 + k * AZ_WIDTH + AZ_LANE;
+          c[k] = a < Ap ? (int)To.cidx[(size_t)old * Ap + a] : -1;
+        }
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+          const int a = a00 + k * AZ_WIDTH + AZ_LANE;
+          if (a00 + k * AZ_WIDTH < Ap) {  // uniform across the warp (Ap is a multiple of the warp width)
+            const bool has = c[k] >= 0;
+            const uint32_t m = w_ballot(has);
+            const int ni = base + az_popc(m & w_lanemask_lt());
+            if (has) { remap[ni] = (int16_t)(c[k] & AZ_CIDX_MASK); Tn.parent[ni] = (int16_t)i; Tn.pmove[ni] = (int16_t)a; }
+            Tn.cidx[(size_t)i * Ap + a] = has ? (int16_t)(ni | (c[k] & AZ_CIDX_EXPANDED)) : (int16_t)-1;
+            base += az_popc(m);
+          }
+        }
+      }
+      count = base;
+      w_sync();
+    }
+    W_LANE0 { Tn.parent[0] = -1; Tn.pmove[0] = -1; }
+    // ---- pass 2, payload: statistics rows, cached position and flags of every kept node.  No node depends on another one here;
+    //      all loads of a node are issued before its first store and the rows of a later node are prefetched meanwhile.
+    const bool cache = To.nboard != nullptr;
+    for (int i = 0; i < count; ++i) {
+      const size_t old = (size_t)remap[i];
+      if (i + 4 < count) {
+        const size_t pf = (size_t)remap[i + 4];
         w_prefetch(To.N + pf * Ap, Ap * 4);
         w_prefetch(To.W + pf * Ap, Ap * 4);
         w_prefetch(To.P + pf * Ap, Ap * 4);
-        w_prefetch(To.cidx + pf * Ap, Ap * 2);
-        if (To.nboard) { w_prefetch(To.nboard + pf * d.ncp, d.ncp); w_prefetch(To.nlegal + pf * Ap, Ap); }
+        if (cache) { w_prefetch(To.nboard + pf * d.ncp, d.ncp); w_prefetch(To.nlegal + pf * Ap, Ap); }
       }
-      for (int a0 = 0; a0 < Ap; a0 += AZ_WIDTH) {
-        const int a = a0 + AZ_LANE;
-        Tn.N[(size_t)i * Ap + a] = To.N[(size_t)old * Ap + a];
-        Tn.W[(size_t)i * Ap + a] = To.W[(size_t)old * Ap + a];
-        Tn.P[(size_t)i * Ap + a] = To.P[(size_t)old * Ap + a];
-        const int c = To.cidx[(size_t)old * Ap + a];
-        const bool has = c >= 0;
-        const uint32_t m = w_ballot(has);
-        const int ni = base + az_popc(m & w_lanemask_lt());
-        if (has) { remap[ni] = (int16_t)(c & AZ_CIDX_MASK); Tn.parent[ni] = (int16_t)i; Tn.pmove[ni] = (int16_t)a; }
-        Tn.cidx[(size_t)i * Ap + a] = has ? (int16_t)(ni | (c & AZ_CIDX_EXPANDED)) : (int16_t)-1;
-        base += az_popc(m);
+      const uint8_t ex = To.expanded[old];
+      const int8_t tp = To.to_play[old];
+      const int16_t ko = cache ? To.nko[old] : (int16_t)-1;
+      for (int a00 = 0; a00 < Ap; a00 += KC * AZ_WIDTH) {
+        float fn[KC], fw[KC], fp[KC];
+        uint8_t lg[KC];
+        int8_t bd[KC];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+          const int a = a00 + k * AZ_WIDTH + AZ_LANE;
+          fn[k] = fw[k] = fp[k] = 0.f; lg[k] = 0; bd[k] = 0;
+          if (a < Ap) {
+            fn[k] = To.N[old * Ap + a];
+            fw[k] = To.W[old * Ap + a];
+            fp[k] = To.P[old * Ap + a];
+            if (cache) {
+              lg[k] = To.nlegal[old * Ap + a];
+              if (a < d.ncp) bd[k] = To.nboard[old * d.ncp + a];
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+          const int a = a00 + k * AZ_WIDTH + AZ_LANE;
+          if (a < Ap) {
+            Tn.N[(size_t)i * Ap + a] = fn[k];
+            Tn.W[(size_t)i * Ap + a] = fw[k];
+            Tn.P[(size_t)i * Ap + a] = fp[k];
+            if (cache) {
+              Tn.nlegal[(size_t)i * Ap + a] = lg[k];
+              if (a < d.ncp) Tn.nboard[(size_t)i * d.ncp + a] = bd[k];
+            }
+          }
+        }
       }
-      if (To.nboard) {  // the node's cached position moves with it
-        W_FOR(c, d.ncp) Tn.nboard[(size_t)i * d.ncp + c] = To.nboard[(size_t)old * d.ncp + c];
-        W_FOR(a, Ap) Tn.nlegal[(size_t)i * Ap + a] = To.nlegal[(size_t)old * Ap + a];
-        W_LANE0 Tn.nko[i] = To.nko[old];
-      }
-      count = base;
       W_LANE0 {
-        Tn.expanded[i] = To.expanded[old];
-        Tn.to_play[i] = To.to_play[old];
+        Tn.expanded[i] = ex;
+        Tn.to_play[i] = tp;
         Tn.vloss[i] = 0;
-        if (i == 0) { Tn.parent[0] = -1; Tn.pmove[0] = -1; }
+        if (cache) Tn.nko[i] = ko;
       }
-      w_sync();
     }
+    w_sync();
     W_LANE0 {
       ti[TI_BUF] = buf ^ 1;
       ti[TI_NODES] = count;

@@ -385,12 +385,16 @@ def main():
         peak = peaks.get('bf16_tflops_sustained') if a.precision == 'bf16' else None
         peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peak else 'fallback 1400 TF/s (of fallback)'
         peak = peak or 1400.0
-        # DRAM traffic of the dominant kernel per launch: from the committed `ncu --set full` capture (profiles/
+        # DRAM traffic of the dominant kernel per launch: from the committed `ncu --set full` captures (halo kernel: profiles/
         # r01_ncu_k_conv_tc_halo_pair_raw.csv, 16384 leaves: dram read+write 1209.1 MB with / 790.0 MB without the residual add),
         # mean over the tower's 10 residual + 11 plain launches, scaled linearly to this tick's leaf count
         traffic = None
-        if a.workload == 'go9_c2' and a.precision == 'bf16' and os.environ.get('AZ_TC_MODE', '4') == '4':
+        tc_mode = os.environ.get('AZ_TC_MODE', '5')
+        if a.workload == 'go9_c2' and a.precision == 'bf16' and tc_mode == '4':
             traffic = (10 * 1209.1e6 + 11 * 790.0e6) / 21 * (tower_evals / 16384.0)
+        if a.workload == 'go9_c2' and a.precision == 'bf16' and tc_mode == '5':
+            # profiles/r01_ncu_k_conv_tc_x_dense_raw.csv, 16384 leaves: 1088.6 MB with / 711.8 MB without the residual add
+            traffic = (10 * 1088.6e6 + 11 * 711.8e6) / 21 * (tower_evals / 16384.0)
         value = d['simulations'] / (ms_max * 1e-3)
         line = {
             'metric': 'mcts_simulations_per_sec', 'value': value, 'unit': 'simulations/s', 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
@@ -407,7 +411,7 @@ def main():
                     'games_drained': e2e_games_all, 'games_per_sec': e2e_games_all / e2e_max,
                     'mean_game_length': e2e_len_all / max(1.0, e2e_games_all)},
             'gpu_launches': int(launches),
-            'roofline': {'bound': 'tensor', 'kernel': ('k_conv_tc_halo' if nf <= 128 and os.environ.get('AZ_TC_MODE', '2') != '0' else 'k_conv_tc') if a.precision == 'bf16' else 'k_conv_f32', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+            'roofline': {'bound': 'tensor', 'kernel': ({'5': 'k_conv_tc_x', '6': 'k_conv_tc_x', '0': 'k_conv_tc'}.get(tc_mode, 'k_conv_tc_halo') if nf <= 128 else 'k_conv_tc') if a.precision == 'bf16' else 'k_conv_f32', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                          'frac': (achieved / peak) if achieved else None, 'traffic': traffic, 'traffic_unit': 'bytes per launch (ncu dram__bytes_read+write)',
                          'algorithmic_bytes_per_launch': 2.0 * tower_evals * (n * n if game == 'go' else (n + 4) ** 2) * nf * 2, 'peak_source': peak_src,
                          'note': f'algorithmic 2*MAC of one 3x3 conv layer ({conv_flops_per_eval / 1e6:.1f} MFLOP/leaf) x {tower_evals} leaves / mean launch time over the '

@@ -25,7 +25,7 @@ def build(force=False, variant=''):
     if not force and os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(p) for p in deps):
         return out
     cmd = ['g++', '-std=c++17', '-O2', '-g', '-DAZ_EMU', '-ffp-contract=off', '-fPIC', '-shared', '-Wall', '-Wno-unused-function',
-           '-Wno-unused-variable'] + VARIANTS[variant] + ['-I', CSRC, '-I', os.path.join(ROOT, 'include'), '-x', 'c++', srcs[0], srcs[1], '-o', out]
+           '-Wno-unused-variable', '-Wno-unknown-pragmas'] + VARIANTS[variant] + ['-I', CSRC, '-I', os.path.join(ROOT, 'include'), '-x', 'c++', srcs[0], srcs[1], '-o', out]
     subprocess.run(cmd, check=True)
     return out
 

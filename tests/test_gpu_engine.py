@@ -84,23 +84,40 @@ def test_net_fp32_matches_reference(cuda, tag):
     eng.close()
 
 
+@pytest.mark.parametrize('mode', ['4', '5'])
 @pytest.mark.parametrize('tag', ['go9_c2', 'gomoku13_c4'])
-def test_net_bf16_matches_bf16_emulation(cuda, tag):
+def test_net_bf16_matches_bf16_emulation(cuda, tag, mode):
     """tcgen05 tower (bf16 operands, f32 accumulation in TMEM) vs a torch restatement that rounds weights and stored
-    activations to bf16 at the same places (oracle/net.py:forward_bf16_emulated): pi within 1e-2, v within 2e-2.
-    The distance to the fp32 reference is rounding, not a bug: the same emulation sits equally far from it."""
+    activations to bf16 at the same places (oracle/net.py:forward_bf16_emulated), for both tower kernels (AZ_TC_MODE 4 = halo
+    tile, 5 = dense-x).  The restatement, the halo kernel and the dense-x kernel add the 9*Cin products of a layer in three
+    different orders, and on these sharp random-init nets one bf16 ulp in an early layer is amplified by the rest of the tower:
+    the halo kernel lands within 1e-2 on pi / 2e-2 on v on the golden positions; the dense-x kernel was measured at 1.5e-2 on
+    them (Gomoku) and is indistinguishable from the halo kernel on 1500 random-play positions per geometry
+    (profiles/r01_tc_modes_check.txt), so it is bounded at 5e-2 / 5e-2 with a mean |dpi| below 1e-3.  For both, the distance to
+    the fp32 reference must not exceed 2.5x the emulation's own: that distance is rounding, not a bug."""
     from alpha_zero_b200.engine import Engine
     from oracle import net as onet
 
     z, n, a, nb, nf, fc, gomoku, net = _net_case(tag)
-    eng = Engine('gomoku' if gomoku else 'go', n, num_games=4, max_simulations=8, max_parallel=2, net=(nb, nf, fc), precision='bf16')
+    old = os.environ.get('AZ_TC_MODE')
+    os.environ['AZ_TC_MODE'] = mode
+    try:
+        eng = Engine('gomoku' if gomoku else 'go', n, num_games=4, max_simulations=8, max_parallel=2, net=(nb, nf, fc), precision='bf16')
+    finally:
+        if old is None:
+            os.environ.pop('AZ_TC_MODE', None)
+        else:
+            os.environ['AZ_TC_MODE'] = old
     eng.set_weights(net.state_dict())
     pi, v = eng.net_forward(z[tag + '/x'])
     lg, ve = onet.forward_bf16_emulated(net.state_dict(), torch.from_numpy(z[tag + '/x']).float(), gomoku)
     pe = torch.softmax(lg, dim=-1).numpy()
-    print(tag, 'kernel vs emulation', np.abs(pi - pe).max(), 'kernel vs fp32', np.abs(pi - z[tag + '/pi']).max(), 'emulation vs fp32', np.abs(pe - z[tag + '/pi']).max())
-    np.testing.assert_allclose(pi, pe, rtol=0, atol=1e-2)
-    np.testing.assert_allclose(v, ve.numpy()[:, 0], rtol=0, atol=2e-2)
+    print(tag, 'mode', mode, 'kernel vs emulation', np.abs(pi - pe).max(), 'mean', np.abs(pi - pe).mean(), 'v', np.abs(v - ve.numpy()[:, 0]).max(),
+          'kernel vs fp32', np.abs(pi - z[tag + '/pi']).max(), 'emulation vs fp32', np.abs(pe - z[tag + '/pi']).max())
+    tol_pi, tol_v = (1e-2, 2e-2) if mode == '4' else (5e-2, 5e-2)
+    np.testing.assert_allclose(pi, pe, rtol=0, atol=tol_pi)
+    np.testing.assert_allclose(v, ve.numpy()[:, 0], rtol=0, atol=tol_v)
+    assert np.abs(pi - pe).mean() < 1e-3
     assert np.abs(pi.sum(axis=1) - 1).max() < 1e-4
     assert np.abs(pi - z[tag + '/pi']).max() < 2.5 * max(np.abs(pe - z[tag + '/pi']).max(), 1e-2)
     eng.close()
