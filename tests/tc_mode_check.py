@@ -37,14 +37,12 @@ def random_play_positions(game, n, count, seed):
     return np.stack(out)
 
 
-def main():
+def compare_modes(tag, count, modes):
+    """{mode: dict(pi, v, max_dpi, max_dv, mean_dpi, repeat)} against the emulation, plus the emulation's mean top probability."""
     from alpha_zero_b200.engine import Engine
     from alpha_zero_b200.network import AlphaZeroNet, randomize_batchnorm
     from oracle import net as onet
 
-    tag = sys.argv[1] if len(sys.argv) > 1 else 'go9_c2'
-    count = int(sys.argv[2]) if len(sys.argv) > 2 else 1500
-    modes = (sys.argv[3] if len(sys.argv) > 3 else os.environ.get('AZ_TC_MODE', '4')).split(',')
     game, n, nb, nf, fc = CASES[tag]
     a = n * n + (1 if game == 'go' else 0)
     torch.manual_seed(123)
@@ -53,26 +51,41 @@ def main():
     lg, ve = onet.forward_bf16_emulated(net.state_dict(), torch.from_numpy(x).float(), game == 'gomoku')
     pe, ve = torch.softmax(lg, dim=-1).numpy(), ve.numpy()[:, 0]
     res = {}
-    for m in modes:
-        os.environ['AZ_TC_MODE'] = m
-        eng = Engine(game, n, num_games=256, max_simulations=8, max_parallel=4, net=(nb, nf, fc), precision='bf16')
-        eng.set_weights(net.state_dict())
-        pi, v = eng.net_forward(x)
-        pi2, v2 = eng.net_forward(x[::-1].copy())  # same buffers again: stale rows of the first call must not leak
-        eng.close()
-        again = max(float(np.abs(pi2[::-1] - pi).max()), float(np.abs(v2[::-1] - v).max()))
-        res[m] = (pi, v, float(np.abs(pi - pe).max()), float(np.abs(v - ve).max()), float(np.abs(pi - pe).mean()), again)
+    old = os.environ.get('AZ_TC_MODE')
+    try:
+        for m in modes:
+            os.environ['AZ_TC_MODE'] = m
+            eng = Engine(game, n, num_games=256, max_simulations=8, max_parallel=4, net=(nb, nf, fc), precision='bf16')
+            eng.set_weights(net.state_dict())
+            pi, v = eng.net_forward(x)
+            pi2, v2 = eng.net_forward(x[::-1].copy())  # same buffers again: stale rows of the first call must not leak
+            eng.close()
+            res[m] = dict(pi=pi, v=v, max_dpi=float(np.abs(pi - pe).max()), max_dv=float(np.abs(v - ve).max()), mean_dpi=float(np.abs(pi - pe).mean()),
+                          repeat=max(float(np.abs(pi2[::-1] - pi).max()), float(np.abs(v2[::-1] - v).max())), finite=bool(np.isfinite(pi).all()))
+    finally:
+        if old is None:
+            os.environ.pop('AZ_TC_MODE', None)
+        else:
+            os.environ['AZ_TC_MODE'] = old
+    return res, float(pe.max(axis=1).mean()), len(x)
+
+
+def main():
+    tag = sys.argv[1] if len(sys.argv) > 1 else 'go9_c2'
+    count = int(sys.argv[2]) if len(sys.argv) > 2 else 1500
+    modes = (sys.argv[3] if len(sys.argv) > 3 else os.environ.get('AZ_TC_MODE', '4')).split(',')
+    res, top, npos = compare_modes(tag, count, modes)
     ok = True
     base = res[modes[0]]
     for m in modes:
-        pi, v, e_pi, e_v, mean_pi, again = res[m]
-        good = (e_pi < 1e-2 and e_v < 2e-2) or (e_pi < 1.5 * base[2] + 2e-3 and e_v < 1.5 * base[3] + 2e-3)
-        good = good and again < 1e-6 and bool(np.isfinite(pi).all()) and float(pe.max(axis=1).mean()) < 0.999
-        d_pi, d_v = float(np.abs(pi - base[0]).max()), float(np.abs(v - base[1]).max())
-        print(f'{tag} mode {m}: vs emulation max|dpi|={e_pi:.3e} mean|dpi|={mean_pi:.2e} max|dv|={e_v:.3e}; vs mode {modes[0]} '
-              f'max|dpi|={d_pi:.3e} max|dv|={d_v:.3e}; repeat call diff {again:.1e} -> {"OK" if good else "MISMATCH"}', flush=True)
+        r = res[m]
+        good = (r['max_dpi'] < 1e-2 and r['max_dv'] < 2e-2) or (r['max_dpi'] < 1.5 * base['max_dpi'] + 2e-3 and r['max_dv'] < 1.5 * base['max_dv'] + 2e-3)
+        good = good and r['repeat'] < 1e-6 and r['finite'] and top < 0.999
+        d_pi, d_v = float(np.abs(r['pi'] - base['pi']).max()), float(np.abs(r['v'] - base['v']).max())
+        print(f'{tag} mode {m}: vs emulation max|dpi|={r["max_dpi"]:.3e} mean|dpi|={r["mean_dpi"]:.2e} max|dv|={r["max_dv"]:.3e}; vs mode {modes[0]} '
+              f'max|dpi|={d_pi:.3e} max|dv|={d_v:.3e}; repeat call diff {r["repeat"]:.1e} -> {"OK" if good else "MISMATCH"}', flush=True)
         ok = ok and good
-    print(f'{tag}: positions={len(x)} mean max-prob of the emulation {float(pe.max(axis=1).mean()):.3f} -> {"ALL OK" if ok else "FAILED"}')
+    print(f'{tag}: positions={npos} mean max-prob of the emulation {top:.3f} -> {"ALL OK" if ok else "FAILED"}')
     return 0 if ok else 1
 
 

@@ -84,17 +84,36 @@ def test_net_fp32_matches_reference(cuda, tag):
     eng.close()
 
 
-@pytest.mark.parametrize('mode', ['4', '5'])
+@pytest.mark.parametrize('tag', ['go9_c2', 'gomoku13_c4', 'go13_128'])
+def test_dense_x_tower_equals_halo_tower_statistically(cuda, tag):
+    """The default tower kernel (dense-x, AZ_TC_MODE=5) against the halo kernel (mode 4) and the bf16 emulation on 1500 positions
+    from random play, 1024 leaves per call (several work units per CTA).  The three add the 9*Cin products of a layer in different
+    orders; on these sharp random-init nets one bf16 ulp in an early layer is amplified by the rest of the tower, so single
+    positions can differ by a lot under ANY order (max |dpi| 0.7-0.8 at 9x9 for both kernels) while the population statistics agree:
+    measured on B200 (profiles/r01_tc_modes_check.txt) mean |dpi| 5.9e-4 vs 6.4e-4 (go9_c2), 3.5e-5 vs 3.4e-5 (gomoku13_c4),
+    3.5e-5 vs 3.5e-5 (go13_128).  Bounds: 1.5x the halo kernel's own distance plus a small absolute slack; repeat calls on the
+    same buffers are bit-identical."""
+    import tc_mode_check
+
+    res, top, npos = tc_mode_check.compare_modes(tag, 1500, ['4', '5'])
+    h, x = res['4'], res['5']
+    print(tag, {m: {k: v for k, v in r.items() if k not in ('pi', 'v')} for m, r in res.items()}, 'mean top probability', top)
+    assert h['finite'] and x['finite'] and h['repeat'] == 0.0 and x['repeat'] == 0.0
+    assert x['mean_dpi'] < 1.5 * h['mean_dpi'] + 1e-4
+    assert x['max_dpi'] < 1.5 * h['max_dpi'] + 1e-2
+    assert x['max_dv'] < 1.5 * h['max_dv'] + 5e-3
+    assert np.abs(x['pi'].sum(axis=1) - 1).max() < 1e-4
+    assert np.abs(x['pi'] - h['pi']).mean() < 2.0 * h['mean_dpi'] + 1e-4  # the two kernels are as close to each other as to the emulation
+
+
+@pytest.mark.parametrize('mode', ['4'])
 @pytest.mark.parametrize('tag', ['go9_c2', 'gomoku13_c4'])
 def test_net_bf16_matches_bf16_emulation(cuda, tag, mode):
     """tcgen05 tower (bf16 operands, f32 accumulation in TMEM) vs a torch restatement that rounds weights and stored
-    activations to bf16 at the same places (oracle/net.py:forward_bf16_emulated), for both tower kernels (AZ_TC_MODE 4 = halo
-    tile, 5 = dense-x).  The restatement, the halo kernel and the dense-x kernel add the 9*Cin products of a layer in three
-    different orders, and on these sharp random-init nets one bf16 ulp in an early layer is amplified by the rest of the tower:
-    the halo kernel lands within 1e-2 on pi / 2e-2 on v on the golden positions; the dense-x kernel was measured at 1.5e-2 on
-    them (Gomoku) and is indistinguishable from the halo kernel on 1500 random-play positions per geometry
-    (profiles/r01_tc_modes_check.txt), so it is bounded at 5e-2 / 5e-2 with a mean |dpi| below 1e-3.  For both, the distance to
-    the fp32 reference must not exceed 2.5x the emulation's own: that distance is rounding, not a bug."""
+    activations to bf16 at the same places (oracle/net.py:forward_bf16_emulated) on the golden positions (3 + 2 of them): pi
+    within 1e-2, v within 2e-2 for the halo kernel (AZ_TC_MODE=4).  With so few positions this is a spot check of one summation
+    order; the default dense-x kernel is compared on a population in test_dense_x_tower_equals_halo_tower_statistically.  The
+    distance to the fp32 reference must not exceed 2.5x the emulation's own: that distance is rounding, not a bug."""
     from alpha_zero_b200.engine import Engine
     from oracle import net as onet
 
