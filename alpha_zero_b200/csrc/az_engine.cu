@@ -44,11 +44,16 @@ struct az_engine {
   float last_net_ms = 0.f;
   int last_net_evals = 0;
   // az_tick_profile: per-phase device time of the self-play tick, CUDA events on the engine stream
+  // AZ_PIPELINE=1 (opt-in): two halves of the slots; the tree kernels of one half run on `tree_rt` while the network evaluates
+  // the other half on `rt`
+  bool pipeline = false;
+  AzRt tree_rt;
   bool prof_on = false;
   double prof_ms[5] = {0, 0, 0, 0, 0};  // collect+compact, network, apply, advance, whole tick
   int prof_ticks = 0;
 #ifndef AZ_EMU
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_net[2] = {nullptr, nullptr}, ev_tree[2] = {nullptr, nullptr}, ev_p0 = nullptr, ev_p1 = nullptr;
   bool collect_occ = false;             // AZ_COLLECT_OCC=1: k_collect built for 7 CTAs per SM (one wave for 4096 games)
   std::vector<cudaEvent_t> prof_ev;     // 5 per tick of the last az_selfplay_tick call
   int prof_pending = 0;                 // ticks recorded and not yet folded into prof_ms
@@ -200,7 +205,7 @@ extern "C" int az_create(const az_config* cfg, az_engine** out) {
   E.priors = dev_alloc<float>(e, rows * d.Ap);
   E.values = dev_alloc<float>(e, rows);
   E.leaf_rows = dev_alloc<int32_t>(e, rows);
-  E.leaf_total = dev_alloc<int32_t>(e, 4);
+  E.leaf_total = dev_alloc<int32_t>(e, 8);  // [0..1] totals, [2] az_net_forward's count, [4..5] totals of the second half (pipeline)
   E.leaf_count = dev_alloc<int32_t>(e, G);
   E.leaf_pk = dev_alloc<int32_t>(e, rows * AZ_PATH);
   E.leaf_pn = dev_alloc<int16_t>(e, rows * AZ_PATH);
@@ -246,6 +251,21 @@ extern "C" int az_create(const az_config* cfg, az_engine** out) {
     e->collect_occ = oc ? atoi(oc) != 0 : e->E.d.node_cache != 0;
   }
 #endif
+  {
+    const char* pl = getenv("AZ_PIPELINE");
+    e->pipeline = pl && atoi(pl) != 0 && d.node_cache && d.G >= 2 && e->net;
+    if (e->pipeline) {
+#ifndef AZ_EMU
+      bool ok = cudaStreamCreateWithFlags(&e->tree_rt.stream, cudaStreamNonBlocking) == cudaSuccess;
+      e->tree_rt.device = e->rt.device;
+      for (int h = 0; h < 2 && ok; ++h)
+        ok = cudaEventCreateWithFlags(&e->ev_net[h], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&e->ev_tree[h], cudaEventDisableTiming) == cudaSuccess;
+      ok = ok && cudaEventCreate(&e->ev_p0) == cudaSuccess && cudaEventCreate(&e->ev_p1) == cudaSuccess;
+      if (!ok) { az_destroy(e); return az_fail(AZ_ERR_CUDA, "az_create: pipeline stream / events"); }
+#endif
+    }
+  }
   // every slot starts as a freshly reset game
   std::vector<int32_t> all(G);
   for (size_t i = 0; i < G; ++i) all[i] = (int32_t)i;
@@ -266,6 +286,13 @@ extern "C" int az_destroy(az_engine* e) {
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   for (cudaEvent_t ev : e->prof_ev) cudaEventDestroy(ev);
+  for (int h = 0; h < 2; ++h) {
+    if (e->ev_net[h]) cudaEventDestroy(e->ev_net[h]);
+    if (e->ev_tree[h]) cudaEventDestroy(e->ev_tree[h]);
+  }
+  if (e->ev_p0) cudaEventDestroy(e->ev_p0);
+  if (e->ev_p1) cudaEventDestroy(e->ev_p1);
+  if (e->tree_rt.stream) { cudaStreamSynchronize(e->tree_rt.stream); cudaStreamDestroy(e->tree_rt.stream); }
 #endif
   rt_destroy(e->rt);
   delete e;
@@ -686,9 +713,73 @@ extern "C" int az_selfplay_restart(az_engine* e, const int32_t* slots, int32_t n
   return rt_sync(e->rt);
 }
 
+// Two-half software pipeline of the tick (AZ_PIPELINE=1).  Games are independent, so the slots are split into halves A and B;
+// per leaf batch:   engine stream:  net(A)            net(B)            net(A) ...
+//                   tree stream:           tree(A)           tree(B)          ...      tree(h) = apply, advance, collect, compact
+// tree(A) of batch t runs while the network evaluates B's leaves of batch t, tree(B) while it evaluates A's of batch t+1: the
+// 20 % of the tick the tree kernels take disappears behind the tensor-core kernels (which leave exactly one 72-register CTA of
+// room per SM, see az_kernels.cuh).  One call still runs n complete leaf batches for every game and leaves every slot in the
+// "after advance" state, like the serial tick: the first collect and the last apply / advance of a call are not overlapped.
+static int selfplay_tick_pipelined(az_engine* e, int n_ticks) {
+  const AzDims& d = e->E.d;
+  const int g0[2] = {0, d.G / 2}, ng[2] = {d.G / 2, d.G - d.G / 2};
+  int32_t* tot[2] = {e->E.leaf_total, e->E.leaf_total + 4};
+  auto collect = [&](int h) {
+    AZ_LAUNCH_WARPS(e->tree_rt, k_collect_r, ng[h], d, e->E, g0[h]);
+#ifdef AZ_EMU
+    k_compact_r(e->E, g0[h], ng[h], tot[h]);
+#else
+    k_compact_r<<<1, 128, 0, e->tree_rt.stream>>>(e->E, g0[h], ng[h], tot[h]);
+    cudaEventRecord(e->ev_tree[h], e->tree_rt.stream);
+#endif
+    e->tree_rt.launches++;
+  };
+#ifndef AZ_EMU
+  // everything queued on the engine stream so far (weights, earlier calls) happens before the tree stream starts
+  cudaEventRecord(e->ev_p0, e->rt.stream);
+  cudaStreamWaitEvent(e->tree_rt.stream, e->ev_p0, 0);
+#endif
+  collect(0);
+  collect(1);
+  for (int t = 0; t < n_ticks; ++t) {
+    for (int h = 0; h < 2; ++h) {
+#ifndef AZ_EMU
+      cudaStreamWaitEvent(e->rt.stream, e->ev_tree[h], 0);
+      if (t == n_ticks - 1 && h == 1) cudaEventRecord(e->ev0, e->rt.stream);
+#endif
+      int rc = aznet_forward(e->net, e->rt, e->E.leaf_obs, e->E.leaf_rows + (size_t)g0[h] * d.Pmax, tot[h], ng[h] * d.Pmax, e->E.priors,
+                             e->E.values, d.Ap);
+      if (rc) return az_fail(rc, "network forward: " + g_az_error);
+#ifndef AZ_EMU
+      if (t == n_ticks - 1 && h == 1) cudaEventRecord(e->ev1, e->rt.stream);
+      cudaEventRecord(e->ev_net[h], e->rt.stream);
+      cudaStreamWaitEvent(e->tree_rt.stream, e->ev_net[h], 0);
+#endif
+      AZ_LAUNCH_WARPS(e->tree_rt, k_apply_r, ng[h], d, e->E, g0[h]);
+      AZ_LAUNCH_WARPS(e->tree_rt, k_advance_r, ng[h], d, e->E, g0[h]);
+      if (t < n_ticks - 1) collect(h);
+#ifndef AZ_EMU
+      else cudaEventRecord(e->ev_tree[h], e->tree_rt.stream);
+#endif
+    }
+  }
+#ifndef AZ_EMU
+  // join: whatever follows on the engine stream (drain, counters, the next call) sees both halves finished
+  cudaStreamWaitEvent(e->rt.stream, e->ev_tree[0], 0);
+  cudaStreamWaitEvent(e->rt.stream, e->ev_tree[1], 0);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return az_fail(AZ_ERR_CUDA, std::string("CUDA launch error: ") + cudaGetErrorString(ce));
+#endif
+  e->rt.launches += e->tree_rt.launches;
+  e->tree_rt.launches = 0;
+  if (e->prof_on) e->prof_ticks += n_ticks;  // phases overlap here: only the tick count is kept, bench.py reads the step time instead
+  return AZ_OK;
+}
+
 extern "C" int az_selfplay_tick(az_engine* e, int32_t n_ticks) {
   if (!e) return az_fail(AZ_ERR_BAD_ARG, "null engine");
   if (!e->selfplay) return az_fail(AZ_ERR_STATE, "az_selfplay_tick: call az_selfplay_begin first");
+  if (e->pipeline && n_ticks > 0) return selfplay_tick_pipelined(e, n_ticks);
   const AzDims& d = e->E.d;
 #ifndef AZ_EMU
   const bool prof = e->prof_on;
@@ -853,7 +944,7 @@ extern "C" int az_last_net_ms(az_engine* e, float* ms, int32_t* n_evals) {
   if (cudaEventElapsedTime(&t, e->ev0, e->ev1) != cudaSuccess) t = 0.f;
   *ms = t;
   int32_t tot[2] = {0, 0};
-  rt_d2h(e->rt, tot, e->E.leaf_total, sizeof(tot));
+  rt_d2h(e->rt, tot, e->E.leaf_total + (e->pipeline ? 4 : 0), sizeof(tot));  // pipeline: the events bracket the second half's tower
   if (n_evals) *n_evals = tot[0];
 #else
   *ms = 0.f;

@@ -333,6 +333,96 @@ __global__ void k_compact(AzState E, int n) {  // one CTA of 1024 threads
 }
 #endif
 
+// ---- slot-range kernels of the two-half pipeline (AZ_PIPELINE=1, az_engine.cu selfplay_tick_pipelined) ------------------
+// The games are split into two halves; while the network evaluates the leaves of one half on the engine stream, the tree
+// kernels of the other half run on a second stream.  Every kernel here is built for 7 CTAs per SM (<= 72 registers, 4 warps):
+// exactly the registers (9216) and shared memory the dense-x conv kernel leaves free on an SM, so that the tree work can be
+// co-resident with the persistent tensor-core kernel instead of waiting for its launch boundaries.
+#ifdef AZ_EMU
+#define AZ_GLOBAL_R static void
+#else
+#define AZ_GLOBAL_R __global__ void __launch_bounds__(AZ_WPB * 32, 7)
+#endif
+
+AZ_GLOBAL_R k_collect_r(AzState E, int g0, int nwarps) {
+  AZ_WARP_INDEX(nwarps) {
+    Sim S;
+    AZ_SCRATCH(E.d, S);
+    LocalCounters lc = {0, 0, 0, 0, 0, 0};
+    game_collect_nc(E, g0 + az_g, S, lc);
+    flush_counters(E, lc);
+  }
+}
+
+AZ_GLOBAL_R k_apply_r(AzState E, int g0, int nwarps) {
+  AZ_WARP_INDEX(nwarps) {
+    LocalCounters lc = {0, 0, 0, 0, 0, 0};
+    game_apply(E, g0 + az_g, lc);
+    flush_counters(E, lc);
+  }
+}
+
+AZ_GLOBAL_R k_advance_r(AzState E, int g0, int nwarps) {
+  AZ_WARP_INDEX(nwarps) {
+    Sim S;
+    AZ_SCRATCH(E.d, S);
+    game_advance(E, g0 + az_g, S);
+  }
+}
+
+// Leaf-row compaction of the slots [g0, g0 + n): rows go to leaf_rows + g0 * Pmax, the totals to tot[0..1].
+#ifdef AZ_EMU
+static void k_compact_r(AzState E, int g0, int n, int32_t* tot) {
+  int total = 0, running = 0;
+  int32_t* rows = E.leaf_rows + (size_t)g0 * E.d.Pmax;
+  for (int g = g0; g < g0 + n; ++g) {
+    const int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
+    const int c = ti[TI_ACTIVE] ? ti[TI_NLEAVES] : 0;
+    E.leaf_count[g] = c;
+    for (int j = 0; j < c; ++j) rows[total++] = g * E.d.Pmax + j;
+    const int st = ti[TI_STATE];
+    if (ti[TI_ACTIVE] && (st == ST_NEED_ROOT || st == ST_SEARCH_INIT || st == ST_SEARCHING)) running++;
+  }
+  tot[0] = total;
+  tot[1] = running;
+}
+#else
+__global__ void __launch_bounds__(128, 7) k_compact_r(AzState E, int g0, int n, int32_t* tot) {  // one CTA of 128 threads
+  __shared__ int s_sum[128];
+  __shared__ int s_run[4];
+  const int t = threadIdx.x;
+  const int per = (n + 127) / 128;
+  const int a = g0 + t * per, b = min(g0 + n, a + per);
+  int32_t* rows = E.leaf_rows + (size_t)g0 * E.d.Pmax;
+  int local = 0, running = 0;
+  for (int g = a; g < b; ++g) {
+    const int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
+    const int c = ti[TI_ACTIVE] ? ti[TI_NLEAVES] : 0;
+    E.leaf_count[g] = c;
+    local += c;
+    const int st = ti[TI_STATE];
+    if (ti[TI_ACTIVE] && (st == ST_NEED_ROOT || st == ST_SEARCH_INIT || st == ST_SEARCHING)) running++;
+  }
+  s_sum[t] = local;
+  running = w_sum_i(running);
+  if ((t & 31) == 0) s_run[t >> 5] = running;
+  __syncthreads();
+  for (int off = 1; off < 128; off <<= 1) {  // Hillis-Steele inclusive scan
+    int v = t >= off ? s_sum[t - off] : 0;
+    __syncthreads();
+    s_sum[t] += v;
+    __syncthreads();
+  }
+  int pos = s_sum[t] - local;
+  for (int g = a; g < b; ++g) {
+    const int c = E.leaf_count[g];
+    for (int j = 0; j < c; ++j) rows[pos++] = g * E.d.Pmax + j;
+  }
+  if (t == 127) tot[0] = s_sum[127];
+  if (t == 0) tot[1] = s_run[0] + s_run[1] + s_run[2] + s_run[3];
+}
+#endif
+
 AZ_GLOBAL k_gather_obs(AzState E, int8_t* dst, long long n) {  // n = total * obs_bytes
   AZ_THREAD_LOOP(i, n) {
     const long long row = i / E.d.obs_bytes, k = i - row * E.d.obs_bytes;

@@ -82,3 +82,52 @@ def test_reference_traces_in_every_variant(libs, node_cache_env, variant, nc, ga
     node_cache_env(nc)
     assert enginecheck.mcts_traces(libs[variant], game) > 50
     enginecheck.concurrent_searches(libs[variant], game)
+
+
+def _games_by_uid(binding, pipeline, game, ticks_per_call):
+    """Self-play on 10 slots; every finished game keyed by its uid -> digest of (record, states, pi, z, moves)."""
+    os.environ['AZ_PIPELINE'] = '1' if pipeline else '0'
+    try:
+        n, A = 9, (82 if game == 'go' else 81)
+        eng = Engine(game, n, num_games=10, max_simulations=32, max_parallel=4, net=(1, 16, 16), precision='fp32', seed=33, max_steps=50 if game == 'go' else 0,
+                     binding=binding)
+    finally:
+        os.environ.pop('AZ_PIPELINE', None)
+    eng.set_weights(_dummy_weights(1, 16, 16, 17, A, 81 if game == 'go' else 169))
+    eng.selfplay_begin(24, 4, warm_up_steps=6, check_resign_after_steps=10, resign_threshold=-0.035, disable_resign_ratio=0.5)
+    out = {}
+    done = 0
+    while done < 420:
+        eng.selfplay_tick(ticks_per_call)
+        done += ticks_per_call
+        games, states, pis, zs = eng.drain_games()
+        mv = eng.last_moves
+        for g in games:
+            s0, ln = g['first_sample'], g['game_length']
+            h = hashlib.sha1()
+            for arr in (states[s0:s0 + ln], pis[s0:s0 + ln], zs[s0:s0 + ln], mv[s0:s0 + ln]):
+                h.update(np.ascontiguousarray(arr).tobytes())
+            h.update(repr(sorted((k, v) for k, v in g.items() if k != 'first_sample')).encode())
+            assert g['reserved'] not in out
+            out[g['reserved']] = h.hexdigest()
+    final = hashlib.sha1()
+    for g in range(10):
+        final.update(eng.env_board(g).tobytes())
+        final.update(repr(sorted(eng.env_scalars(g).items())).encode())
+    c = eng.counters()
+    eng.close()
+    assert c['errors'] == 0
+    return out, final.hexdigest(), {k: c[k] for k in ('simulations', 'evaluations', 'moves', 'games', 'nodes', 'depth_sum', 'descents', 'samples')}
+
+
+@pytest.mark.parametrize('game', ['go', 'gomoku'])
+def test_two_half_pipeline_plays_the_same_games(libs, node_cache_env, game):
+    """AZ_PIPELINE=1 (tree kernels of one half of the slots overlapped with the network of the other half) runs the same n leaf
+    batches per call for every game: every finished game, the final positions and all counters equal the serial tick's, for
+    different call granularities (the order in which finished games reach the ring may differ, hence the comparison by game id)."""
+    node_cache_env(1)
+    ref = _games_by_uid(libs[''], False, game, 7)
+    assert len(ref[0]) >= 8
+    for ticks_per_call in (7, 1, 20):
+        got = _games_by_uid(libs[''], True, game, ticks_per_call)
+        assert got == ref, (ticks_per_call, got[2], ref[2])
