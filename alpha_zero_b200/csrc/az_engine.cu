@@ -862,9 +862,46 @@ extern "C" int az_drain_games(az_engine* e, az_game_record* records, int32_t max
   const unsigned long long head = c[CT_GAMES_HEAD];
   if (head - e->drained_games > AZ_GAMES_RING) e->drained_games = head - AZ_GAMES_RING;
   int ng = 0, ns = 0;
-  while (e->drained_games < head && ng < max_games) {
-    int32_t gr[GR_INTS];
-    rt_d2h(e->rt, gr, e->E.games_ring + (size_t)(e->drained_games % AZ_GAMES_RING) * GR_INTS, sizeof(gr));
+  // all pending game records in one or two copies (the ring of records is contiguous modulo its size)
+  const unsigned long long pending = head - e->drained_games;
+  std::vector<int32_t> recs((size_t)pending * GR_INTS);
+  if (pending) {
+    const size_t r0 = (size_t)(e->drained_games % AZ_GAMES_RING);
+    const size_t k1 = std::min((size_t)pending, (size_t)AZ_GAMES_RING - r0), k2 = (size_t)pending - k1;
+    rt_d2h_async(e->rt, recs.data(), e->E.games_ring + r0 * GR_INTS, k1 * GR_INTS * sizeof(int32_t));
+    if (k2) rt_d2h_async(e->rt, recs.data() + k1 * GR_INTS, e->E.games_ring, k2 * GR_INTS * sizeof(int32_t));
+    rc = rt_sync(e->rt);
+    if (rc) return rc;
+  }
+  // Games finish one after the other, so the samples of consecutive games are consecutive in the sample ring: the accepted
+  // games are copied as maximal contiguous runs (normally ONE run per call: two copies per array when it wraps) instead of
+  // game by game.
+  unsigned long long run_first = 0;
+  int run_len = 0, run_dst = 0;
+  auto flush_run = [&]() {
+    if (!run_len) return;
+    const size_t s0 = (size_t)(run_first % (unsigned long long)d.ring_cap);
+    const size_t n1 = std::min((size_t)run_len, (size_t)d.ring_cap - s0), n2 = (size_t)run_len - n1;
+    if (states) {
+      rt_d2h_async(e->rt, states + (size_t)run_dst * d.obs_bytes, e->E.r_obs + s0 * d.obs_bytes, n1 * d.obs_bytes);
+      if (n2) rt_d2h_async(e->rt, states + (size_t)(run_dst + n1) * d.obs_bytes, e->E.r_obs, n2 * d.obs_bytes);
+    }
+    if (pis) {
+      rt_d2h_async(e->rt, pis + (size_t)run_dst * d.A, e->E.r_pi + s0 * d.A, n1 * d.A * sizeof(float));
+      if (n2) rt_d2h_async(e->rt, pis + (size_t)(run_dst + n1) * d.A, e->E.r_pi, n2 * d.A * sizeof(float));
+    }
+    if (values) {
+      rt_d2h_async(e->rt, values + run_dst, e->E.r_z + s0, n1 * sizeof(float));
+      if (n2) rt_d2h_async(e->rt, values + run_dst + n1, e->E.r_z, n2 * sizeof(float));
+    }
+    if (moves) {
+      rt_d2h_async(e->rt, moves + run_dst, e->E.r_move + s0, n1 * sizeof(int16_t));
+      if (n2) rt_d2h_async(e->rt, moves + run_dst + n1, e->E.r_move, n2 * sizeof(int16_t));
+    }
+    run_len = 0;
+  };
+  for (unsigned long long k = 0; k < pending && ng < max_games; ++k) {
+    const int32_t* gr = recs.data() + (size_t)k * GR_INTS;
     const int len = gr[GR_LEN];
     if (ns + len > max_samples) break;
     if (records) {
@@ -888,29 +925,16 @@ extern "C" int az_drain_games(az_engine* e, az_game_record* records, int32_t max
       e->drained_games++;
       continue;
     }
-    // the samples of one game are contiguous in the ring (modulo wrap): at most two copies per array
-    const size_t s0 = (size_t)(first % (unsigned long long)d.ring_cap);
-    const size_t n1 = std::min((size_t)len, (size_t)d.ring_cap - s0), n2 = (size_t)len - n1;
-    if (states) {
-      rt_d2h(e->rt, states + (size_t)ns * d.obs_bytes, e->E.r_obs + s0 * d.obs_bytes, n1 * d.obs_bytes);
-      if (n2) rt_d2h(e->rt, states + (size_t)(ns + n1) * d.obs_bytes, e->E.r_obs, n2 * d.obs_bytes);
-    }
-    if (pis) {
-      rt_d2h(e->rt, pis + (size_t)ns * d.A, e->E.r_pi + s0 * d.A, n1 * d.A * sizeof(float));
-      if (n2) rt_d2h(e->rt, pis + (size_t)(ns + n1) * d.A, e->E.r_pi, n2 * d.A * sizeof(float));
-    }
-    if (values) {
-      rt_d2h(e->rt, values + ns, e->E.r_z + s0, n1 * sizeof(float));
-      if (n2) rt_d2h(e->rt, values + ns + n1, e->E.r_z, n2 * sizeof(float));
-    }
-    if (moves) {
-      rt_d2h(e->rt, moves + ns, e->E.r_move + s0, n1 * sizeof(int16_t));
-      if (n2) rt_d2h(e->rt, moves + ns + n1, e->E.r_move, n2 * sizeof(int16_t));
-    }
+    if (run_len && first != run_first + (unsigned long long)run_len) flush_run();
+    if (!run_len) { run_first = first; run_dst = ns; }
+    run_len += len;
     ns += len;
     ng++;
     e->drained_games++;
   }
+  flush_run();
+  rc = rt_sync(e->rt);
+  if (rc) return rc;
   *n_games = ng;
   *n_samples = ns;
   return AZ_OK;

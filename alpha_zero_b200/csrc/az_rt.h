@@ -28,6 +28,7 @@ static inline void* rt_alloc(size_t bytes) { return calloc(bytes ? bytes : 1, 1)
 static inline void rt_free(void* p) { free(p); }
 static inline void rt_h2d(AzRt&, void* dst, const void* src, size_t n) { memcpy(dst, src, n); }
 static inline void rt_d2h(AzRt&, void* dst, const void* src, size_t n) { memcpy(dst, src, n); }
+static inline void rt_d2h_async(AzRt&, void* dst, const void* src, size_t n) { memcpy(dst, src, n); }
 static inline void rt_d2d(AzRt&, void* dst, const void* src, size_t n) { memmove(dst, src, n); }
 static inline void rt_zero(AzRt&, void* dst, size_t n) { memset(dst, 0, n); }
 static inline int rt_sync(AzRt&) { return 0; }
@@ -77,6 +78,10 @@ static inline void rt_h2d(AzRt& rt, void* dst, const void* src, size_t n) {
 static inline void rt_d2h(AzRt& rt, void* dst, const void* src, size_t n) {
   cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, rt.stream);
   cudaStreamSynchronize(rt.stream);
+}
+// queued only: the caller synchronises the stream (rt_sync) before reading dst
+static inline void rt_d2h_async(AzRt& rt, void* dst, const void* src, size_t n) {
+  cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, rt.stream);
 }
 static inline void rt_d2d(AzRt& rt, void* dst, const void* src, size_t n) {
   cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, rt.stream);
