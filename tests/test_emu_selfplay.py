@@ -168,3 +168,34 @@ def test_bench_population_stagger(emu):
     spm = (c1['simulations'] - c0['simulations']) / max(1, c1['moves'] - c0['moves'])
     assert c1['errors'] == 0 and 12.0 < spm < 21.0, spm
     eng.close()
+
+
+def test_drain_in_pieces_equals_drain_at_once(emu):
+    """az_drain_games copies the samples of consecutive games as contiguous runs of the ring; draining game by game, with a tight
+    sample budget, or all at once must hand out the same games with the same samples (small ring: the runs wrap)."""
+    def play(drain):
+        eng = Engine('go', 9, num_games=8, max_simulations=16, max_parallel=4, net=(1, 16, 16), precision='fp32', max_steps=24, seed=17,
+                     sample_ring=600, binding=emu)
+        eng.set_weights(_dummy_weights(1, 16, 16, 17, 82, 81))
+        eng.selfplay_begin(12, 4, warm_up_steps=6, check_resign_after_steps=8, resign_threshold=-1.0, disable_resign_ratio=1.0)
+        out = []
+        for rnd in range(30):
+            eng.selfplay_tick(12)
+            while True:
+                games, states, pis, zs = drain(eng)
+                if not games:
+                    break
+                mv = eng.last_moves
+                for g in games:
+                    s0, ln = g['first_sample'], g['game_length']
+                    out.append((g['reserved'], g['slot'], ln, g['winner'], states[s0:s0 + ln].tobytes(), pis[s0:s0 + ln].tobytes(), zs[s0:s0 + ln].tobytes(),
+                                mv[s0:s0 + ln].tobytes()))
+        c = eng.counters()
+        eng.close()
+        assert c['ring_dropped'] == 0 and c['games'] == len(out) and c['samples'] == sum(o[2] for o in out)
+        return out
+
+    whole = play(lambda e: e.drain_games())
+    assert len(whole) > 16
+    assert play(lambda e: e.drain_games(max_games=1)) == whole
+    assert play(lambda e: e.drain_games(max_games=3, max_samples=60)) == whole
