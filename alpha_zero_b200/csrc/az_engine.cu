@@ -213,7 +213,7 @@ extern "C" int az_create(const az_config* cfg, az_engine** out) {
   E.res_pi = dev_alloc<double>(e, G * d.Ap);
   E.res_q = dev_alloc<double>(e, G * 2);
   E.res_move = dev_alloc<int32_t>(e, G);
-  E.g_obs = dev_alloc<int8_t>(e, G * d.max_len * d.obs_bytes);
+  E.g_obs = dev_alloc<int8_t>(e, G * d.max_len * d.obs_bytes + 16);  // + slack: w_copy_bytes reads whole aligned words of the record
   E.g_pi = dev_alloc<float>(e, G * d.max_len * d.A);
   E.g_to_play = dev_alloc<int8_t>(e, G * d.max_len);
   E.g_move = dev_alloc<int16_t>(e, G * d.max_len);
