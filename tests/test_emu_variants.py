@@ -62,7 +62,7 @@ def _trajectory(binding, game, n, sims, par, ticks, num_stack=8):
     return h.hexdigest(), {k: c[k] for k in ('simulations', 'evaluations', 'moves', 'games', 'nodes', 'depth_sum', 'descents', 'samples')}
 
 
-@pytest.mark.parametrize('case', [('go', 9, 96, 4, 8), ('go', 9, 40, 1, 8), ('gomoku', 9, 64, 4, 8), ('go', 5, 64, 8, 3)])
+@pytest.mark.parametrize('case', [('go', 9, 96, 4, 8), ('go', 9, 40, 1, 8), ('gomoku', 9, 64, 4, 8), ('go', 5, 64, 8, 3), ('go', 19, 48, 4, 8), ('gomoku', 13, 48, 8, 8)])
 def test_node_cache_and_deep_paths_give_identical_selfplay(libs, node_cache_env, case):
     game, n, sims, par, num_stack = case
     out = {}
@@ -73,7 +73,8 @@ def test_node_cache_and_deep_paths_give_identical_selfplay(libs, node_cache_env,
     base = out[('', 0)]
     for k, v in out.items():
         assert v == base, (k, v, base)
-    assert base[1]['depth_sum'] / base[1]['descents'] > 2.2  # mean leaf depth: a good share of the descents passes the deep build's 3 recorded plies
+    if n <= 9:  # mean leaf depth: a good share of the descents passes the deep build's 3 recorded plies (wide boards search broadly)
+        assert base[1]['depth_sum'] / base[1]['descents'] > 2.2
 
 
 @pytest.mark.parametrize('variant,nc', [('', 1), ('deep', 0), ('deep', 1)])
