@@ -51,3 +51,27 @@ def all_gather_samples(states, pis, zs, capacity, device=None, group=None):
     P = np.concatenate([out_p[r, :c] for r, c in enumerate(counts)], axis=0)
     Z = np.concatenate([zz[r, :c] for r, c in enumerate(counts)], axis=0)
     return S, P, Z, kept
+
+
+class SampleGatherer:
+    """One all-gather per collection round with a fixed block per rank; what does not fit the block waits for the next round
+    (finished games come in waves, the collective shape stays static).  `push` returns every rank's samples of this round."""
+
+    def __init__(self, capacity, device=None, group=None):
+        self.capacity, self.device, self.group = int(capacity), device, group
+        self._backlog = None
+        self.total = 0
+
+    def pending(self):
+        return 0 if self._backlog is None else len(self._backlog[2])
+
+    def push(self, states, pis, zs):
+        if self._backlog is not None:
+            b = self._backlog
+            states, pis, zs = np.concatenate([b[0], states]), np.concatenate([b[1], pis]), np.concatenate([b[2], zs])
+            self._backlog = None
+        S, P, Z, kept = all_gather_samples(states, pis, zs, self.capacity, device=self.device, group=self.group)
+        if kept:
+            self._backlog = (states[-kept:], pis[-kept:], zs[-kept:])
+        self.total += len(Z)
+        return S, P, Z

@@ -287,22 +287,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    backlog = []
+    gatherer = None
+    if dist is not None:
+        from alpha_zero_b200.gather import SampleGatherer
+
+        gatherer = SampleGatherer(capacity=G * 2, device=f'cuda:{local}')
 
     def gather_samples(states, pis, zs):
         """NCCL all-gather of the (state, pi, z) samples produced this step: fixed-capacity blocks + counts; what
         does not fit the block waits for the next step."""
-        if dist is None:
+        if gatherer is None:
             return len(zs)
-        from alpha_zero_b200.gather import all_gather_samples
-
-        if backlog:
-            b = backlog.pop()
-            states, pis, zs = np.concatenate([b[0], states]), np.concatenate([b[1], pis]), np.concatenate([b[2], zs])
-        S, P, Z, kept = all_gather_samples(states, pis, zs, capacity=G * 2, device=f'cuda:{local}')
-        if kept:
-            backlog.append((states[-kept:], pis[-kept:], zs[-kept:]))
-        return len(Z)
+        return len(gatherer.push(states, pis, zs)[2])
 
     # ---- warm-up --------------------------------------------------------------------------------
     for _ in range(a.warmup):

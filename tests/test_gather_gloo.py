@@ -22,7 +22,13 @@ def _worker(rank, world, port, out):
     z = rng.choice([-1.0, 0.0, 1.0], size=n).astype(np.float32)
     S, P, Z, kept = all_gather_samples(st, pi, z, capacity=16)
     S2, P2, Z2, kept2 = all_gather_samples(st[:0], pi[:0], z[:0], capacity=4)  # empty contribution from every rank
-    out.put((rank, lo, hi, S.shape, float(S.sum()), float(P.sum()), Z.tolist(), kept, S2.shape[0], float(st.sum()), float(pi.sum()), z.tolist()))
+    # bench.py's exchange: a block of 6 samples per rank and round, the rest waits; three rounds, the last two with nothing new
+    from alpha_zero_b200.gather import SampleGatherer
+
+    gt = SampleGatherer(capacity=6)
+    rounds = [gt.push(st, pi, z)] + [gt.push(st[:0], pi[:0], z[:0]) for _ in range(2)]
+    carried = ([r[2].tolist() for r in rounds], [r[0].shape for r in rounds], gt.pending(), gt.total)
+    out.put((rank, lo, hi, S.shape, float(S.sum()), float(P.sum()), Z.tolist(), kept, S2.shape[0], float(st.sum()), float(pi.sum()), z.tolist(), carried))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -46,3 +52,7 @@ def test_all_gather_samples_world2():
         assert r[3] == (5 + 12, 17, 9, 9) and r[7] == 0 and r[8] == 0
         assert abs(r[4] - (r0[9] + r1[9])) < 1e-3 and abs(r[5] - (r0[10] + r1[10])) < 1e-2
         assert r[6] == r0[11] + r1[11]  # rank order preserved
+        # rank 0 holds 5 samples, rank 1 holds 12: round 1 moves 5 + 6, round 2 the next 6 of rank 1, round 3 nothing; order kept
+        zs_rounds, shapes, pending, total = r[12]
+        assert zs_rounds[0] == r0[11] + r1[11][:6] and zs_rounds[1] == r1[11][6:] and zs_rounds[2] == []
+        assert shapes[0] == (11, 17, 9, 9) and shapes[1] == (6, 17, 9, 9) and pending == 0 and total == 17
