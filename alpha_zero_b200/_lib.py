@@ -12,7 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libaz_b200.so')
 
 GAME_GO, GAME_GOMOKU = 0, 1
-NET_FP32, NET_BF16 = 0, 1
+NET_FP32, NET_BF16, NET_BF16X3 = 0, 1, 2
+PRECISIONS = {'fp32': NET_FP32, 'bf16': NET_BF16, 'bf16x3': NET_BF16X3}
 ERR_INVALID_ACTION, ERR_ILLEGAL_ACTION, ERR_GAME_OVER, ERR_BAD_ARG = -2, -3, -4, -5
 
 
@@ -51,11 +52,11 @@ class AzGameRecord(C.Structure):
 # every symbol include/az_engine.h declares; tests/test_abi.py checks the shared library exports each one
 SYMBOLS = [
     'az_last_error', 'az_version', 'az_create', 'az_destroy', 'az_get_config', 'az_num_actions', 'az_obs_bytes',
-    'az_set_weights', 'az_net_forward', 'az_env_reset', 'az_env_step', 'az_env_observation', 'az_env_legal_actions',
+    'az_set_weights', 'az_net_forward', 'az_net_conv_layer', 'az_net_info', 'az_env_reset', 'az_env_step', 'az_env_observation', 'az_env_legal_actions',
     'az_env_board', 'az_env_scalars', 'az_env_score', 'az_env_copy', 'az_env_state_bytes', 'az_env_export',
     'az_env_import', 'az_env_replay', 'az_search_begin', 'az_search_select', 'az_search_apply', 'az_search_result', 'az_search_commit',
     'az_search_run', 'az_selfplay_begin', 'az_selfplay_tick', 'az_selfplay_update', 'az_selfplay_restart', 'az_sync', 'az_get_counters', 'az_drain_games',
-    'az_sample_ring_device', 'az_stream', 'az_last_net_ms', 'az_tick_profile', 'az_replay_create', 'az_replay_ingest', 'az_replay_add', 'az_replay_info',
+    'az_gather_pack', 'az_host_alloc', 'az_host_free', 'az_stream', 'az_last_net_ms', 'az_tick_profile', 'az_replay_create', 'az_replay_ingest', 'az_replay_add', 'az_replay_info',
     'az_replay_sample',
 ]
 

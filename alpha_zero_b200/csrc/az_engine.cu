@@ -23,6 +23,7 @@ struct az_engine {
   AzRt rt;
   AzState E;
   std::vector<void*> allocs;
+  size_t alloc_bytes = 0, alloc_failed = 0;  // dev_alloc bookkeeping: bytes held, size of the first failed request
   AzNet* net = nullptr;
   // staging
   int32_t *d_slots = nullptr, *d_aux = nullptr, *d_out = nullptr;
@@ -88,12 +89,36 @@ static void prof_fold(az_engine* e) {
 }
 #endif
 
+// Every device buffer of the engine comes from here; a failure is remembered (first failing request and the running total) and
+// checked once after a group of allocations, so that a partial out-of-memory can never hand a null buffer to a kernel.
 template <class T>
 static T* dev_alloc(az_engine* e, size_t count) {
-  void* p = rt_alloc(count * sizeof(T));
-  if (p) e->allocs.push_back(p);
+  const size_t bytes = count * sizeof(T);
+  void* p = rt_alloc(bytes);
+  if (p) {
+    e->allocs.push_back(p);
+    e->alloc_bytes += bytes;
+  } else if (!e->alloc_failed) {
+    e->alloc_failed = bytes ? bytes : 1;
+  }
   return (T*)p;
 }
+
+static int alloc_check(az_engine* e, const char* where) {
+  if (!e->alloc_failed) return AZ_OK;
+  const size_t want = e->alloc_failed;
+  e->alloc_failed = 0;
+  return az_fail(AZ_ERR_CUDA, std::string(where) + ": device allocation of " + std::to_string(want) + " bytes failed (" +
+                                  std::to_string(e->alloc_bytes >> 20) + " MB already held by this engine)");
+}
+
+// One engine is bound to one CUDA device, but the calling thread's current device may be anything (another thread of the
+// process, torch.cuda.set_device): every entry point makes the engine's device current before it allocates or launches.
+#ifndef AZ_EMU
+#define AZ_ENTER(e) do { if (e) cudaSetDevice((e)->rt.device); } while (0)
+#else
+#define AZ_ENTER(e) do { } while (0)
+#endif
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
@@ -158,6 +183,14 @@ extern "C" int az_create(const az_config* cfg, az_engine** out) {
     double want = 2.0 * (double)d.G * (double)d.max_len;
     const double cap_bytes = 8.0 * 1024 * 1024 * 1024;
     if (want * per_sample > cap_bytes) want = std::max((double)d.G * d.max_len, cap_bytes / per_sample);
+#ifndef AZ_EMU
+    {
+      // never ask for more than a quarter of what the device has free right now (several actors may share one GPU)
+      size_t free_b = 0, total_b = 0;
+      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && want * per_sample > 0.25 * (double)free_b)
+        want = std::max((double)d.G * 8.0, 0.25 * (double)free_b / per_sample);
+    }
+#endif
     d.ring_cap = cfg->sample_ring > 0 ? cfg->sample_ring : (int)std::min(want, 2.0e9);
   }
   e->cfg.max_steps = d.max_steps;
@@ -191,7 +224,6 @@ extern "C" int az_create(const az_config* cfg, az_engine** out) {
       E.nboard = dev_alloc<int8_t>(e, nodes * d.ncp);
       E.nlegal = dev_alloc<uint8_t>(e, nodes * d.Ap);
       E.nko = dev_alloc<int16_t>(e, nodes);
-      if (!E.nko) { az_destroy(e); return az_fail(AZ_ERR_CUDA, "az_create: device allocation failed (node cache)"); }
     }
   }
   e->d_pbc_fresh = dev_alloc<double>(e, d.table_len);
@@ -231,10 +263,8 @@ extern "C" int az_create(const az_config* cfg, az_engine** out) {
   e->d_stage_obs = dev_alloc<int8_t>(e, rows * d.obs_bytes);
   e->d_stage_pri = dev_alloc<float>(e, rows * d.A);
   e->d_stage_val = dev_alloc<float>(e, rows);
-  if (!E.counters || !e->d_stage_val || !E.cidx || !E.g_obs) {
-    az_destroy(e);
-    return az_fail(AZ_ERR_CUDA, "az_create: device allocation failed");
-  }
+  rc = alloc_check(e, "az_create");
+  if (rc) { az_destroy(e); return rc; }
   memset(&E.s, 0, sizeof(E.s));
   E.s.seed = cfg->seed;
   if (cfg->num_filters > 0) {
@@ -278,6 +308,7 @@ extern "C" int az_create(const az_config* cfg, az_engine** out) {
 }
 
 extern "C" int az_destroy(az_engine* e) {
+  AZ_ENTER(e);
   if (!e) return AZ_OK;
   rt_sync(e->rt);
   if (e->net) aznet_destroy(e->net);
@@ -300,6 +331,7 @@ extern "C" int az_destroy(az_engine* e) {
 }
 
 extern "C" int az_get_config(az_engine* e, az_config* out) {
+  AZ_ENTER(e);
   if (!e || !out) return az_fail(AZ_ERR_BAD_ARG, "null argument");
   *out = e->cfg;
   return AZ_OK;
@@ -323,6 +355,7 @@ static int upload_slots(az_engine* e, const int32_t* slots, int n) {
 
 // ---- weights / network ---------------------------------------------------------------------------
 extern "C" int az_set_weights(az_engine* e, const float* const* tensors, const int64_t* numel, int32_t n_tensors) {
+  AZ_ENTER(e);
   if (!e || !tensors || !numel) return az_fail(AZ_ERR_BAD_ARG, "null argument");
   if (!e->net) return az_fail(AZ_ERR_STATE, "engine was created without a network (num_filters == 0)");
   std::string err;
@@ -332,6 +365,7 @@ extern "C" int az_set_weights(az_engine* e, const float* const* tensors, const i
 }
 
 extern "C" int az_net_forward(az_engine* e, const int8_t* obs, int32_t n, float* priors, float* values) {
+  AZ_ENTER(e);
   if (!e || !obs || !priors || !values) return az_fail(AZ_ERR_BAD_ARG, "null argument");
   if (!e->net || !aznet_ready(e->net)) return az_fail(AZ_ERR_STATE, "network weights not set");
   const AzDims& d = e->E.d;
@@ -351,8 +385,29 @@ extern "C" int az_net_forward(az_engine* e, const int8_t* obs, int32_t n, float*
   return rt_sync(e->rt);
 }
 
+extern "C" int az_net_conv_layer(az_engine* e, int32_t layer, const float* in, const float* res, int32_t n, float* out) {
+  AZ_ENTER(e);
+  if (!e || !in || !out) return az_fail(AZ_ERR_BAD_ARG, "null argument");
+  if (!e->net || !aznet_ready(e->net)) return az_fail(AZ_ERR_STATE, "network weights not set");
+  std::string err;
+  int rc = aznet_debug_layer(e->net, e->rt, layer, in, res, n, out, err);
+  if (rc) return az_fail(rc, "az_net_conv_layer: " + err);
+  return AZ_OK;
+}
+
+extern "C" int az_net_info(az_engine* e, int32_t* tc_mode, int32_t* padded_filters, double* flops_per_eval) {
+  AZ_ENTER(e);
+  if (!e) return az_fail(AZ_ERR_BAD_ARG, "null engine");
+  if (!e->net) return az_fail(AZ_ERR_STATE, "engine was created without a network (num_filters == 0)");
+  if (tc_mode) *tc_mode = aznet_tc_mode_of(e->net);
+  if (padded_filters) *padded_filters = aznet_padded_filters(e->net);
+  if (flops_per_eval) *flops_per_eval = aznet_flops_per_eval(e->net);
+  return AZ_OK;
+}
+
 // ---- BoardGameEnv ----------------------------------------------------------------------------------
 extern "C" int az_env_reset(az_engine* e, const int32_t* slots, int32_t n) {
+  AZ_ENTER(e);
   int rc = upload_slots(e, slots, n);
   if (rc) return rc;
   AZ_LAUNCH_WARPS(e->rt, k_env_reset, n, e->E.d, e->E, e->d_slots);
@@ -360,6 +415,7 @@ extern "C" int az_env_reset(az_engine* e, const int32_t* slots, int32_t n) {
 }
 
 extern "C" int az_env_step(az_engine* e, const int32_t* slots, const int32_t* actions, int32_t n, float* rewards, int32_t* dones) {
+  AZ_ENTER(e);
   int rc = upload_slots(e, slots, n);
   if (rc) return rc;
   if (!actions) return az_fail(AZ_ERR_BAD_ARG, "null actions");
@@ -383,6 +439,7 @@ extern "C" int az_env_step(az_engine* e, const int32_t* slots, const int32_t* ac
 
 extern "C" int az_env_replay(az_engine* e, const int32_t* slots, int32_t n, const int16_t* moves, const int32_t* offsets, int8_t* states,
                              int32_t* n_played, int32_t* status) {
+  AZ_ENTER(e);
   int rc = upload_slots(e, slots, n);
   if (rc) return rc;
   if (!moves || !offsets || !n_played || !status) return az_fail(AZ_ERR_BAD_ARG, "null argument");
@@ -415,6 +472,7 @@ extern "C" int az_env_replay(az_engine* e, const int32_t* slots, int32_t n, cons
 }
 
 extern "C" int az_env_observation(az_engine* e, int32_t slot, int8_t* out) {
+  AZ_ENTER(e);
   int rc = check_slot(e, slot);
   if (rc) return rc;
   AZ_LAUNCH_WARPS(e->rt, k_env_obs, 1, e->E.d, e->E, slot, e->d_stage_obs);
@@ -423,6 +481,7 @@ extern "C" int az_env_observation(az_engine* e, int32_t slot, int8_t* out) {
 }
 
 extern "C" int az_env_legal_actions(az_engine* e, int32_t slot, uint8_t* out) {
+  AZ_ENTER(e);
   int rc = check_slot(e, slot);
   if (rc) return rc;
   rt_d2h(e->rt, out, e->E.root_legal + (size_t)slot * e->E.d.Ap, e->E.d.A);
@@ -430,6 +489,7 @@ extern "C" int az_env_legal_actions(az_engine* e, int32_t slot, uint8_t* out) {
 }
 
 extern "C" int az_env_board(az_engine* e, int32_t slot, int8_t* out) {
+  AZ_ENTER(e);
   int rc = check_slot(e, slot);
   if (rc) return rc;
   const AzDims& d = e->E.d;
@@ -443,6 +503,7 @@ extern "C" int az_env_board(az_engine* e, int32_t slot, int8_t* out) {
 static int ext_player(const AzDims& d, int v) { return (d.game == AZ_GAME_GOMOKU && v == -1) ? 2 : v; }
 
 extern "C" int az_env_scalars(az_engine* e, int32_t slot, int32_t* out) {
+  AZ_ENTER(e);
   int rc = check_slot(e, slot);
   if (rc) return rc;
   int32_t ei[ENV_INTS];
@@ -463,6 +524,7 @@ extern "C" int az_env_scalars(az_engine* e, int32_t slot, int32_t* out) {
 }
 
 extern "C" int az_env_score(az_engine* e, int32_t slot, float* out_score) {
+  AZ_ENTER(e);
   int rc = check_slot(e, slot);
   if (rc) return rc;
   AZ_LAUNCH_WARPS(e->rt, k_env_score, 1, e->E.d, e->E, slot, e->d_fout);
@@ -471,6 +533,7 @@ extern "C" int az_env_score(az_engine* e, int32_t slot, float* out_score) {
 }
 
 extern "C" int az_env_copy(az_engine* e, int32_t src, int32_t dst) {
+  AZ_ENTER(e);
   int rc = check_slot(e, src);
   if (!rc) rc = check_slot(e, dst);
   if (rc) return rc;
@@ -480,12 +543,14 @@ extern "C" int az_env_copy(az_engine* e, int32_t src, int32_t dst) {
 }
 
 extern "C" int az_env_state_bytes(az_engine* e) {
+  AZ_ENTER(e);
   if (!e) return AZ_ERR_BAD_ARG;
   const AzDims& d = e->E.d;
   return d.ncp * 9 + ENV_INTS * 4 + d.Ap;
 }
 
 extern "C" int az_env_export(az_engine* e, int32_t slot, uint8_t* out) {
+  AZ_ENTER(e);
   int rc = check_slot(e, slot);
   if (rc) return rc;
   const AzDims& d = e->E.d;
@@ -497,6 +562,7 @@ extern "C" int az_env_export(az_engine* e, int32_t slot, uint8_t* out) {
 }
 
 extern "C" int az_env_import(az_engine* e, int32_t slot, const uint8_t* in) {
+  AZ_ENTER(e);
   int rc = check_slot(e, slot);
   if (rc) return rc;
   const AzDims& d = e->E.d;
@@ -516,12 +582,14 @@ static int set_search_cfg(az_engine* e, const az_search_params* p) {
   const int P = p->num_parallel > 1 ? p->num_parallel : 1;
   const AzDims& d = e->E.d;
   if (P > d.Pmax) return az_fail(AZ_ERR_CAPACITY, "num_parallel exceeds the engine's max_parallel");
-  AzSearchCfg& s = e->E.s;
+  const int sims_bound = p->num_simulations + (P > 1 ? P : 0);
+  if (sims_bound + 4 * P + 16 > d.cap) return az_fail(AZ_ERR_CAPACITY, "num_simulations exceeds the engine's node pool (max_simulations)");
+  if (!(p->c_puct_base > 0.0)) return az_fail(AZ_ERR_BAD_ARG, "c_puct_base must be positive");
+  AzSearchCfg& s = e->E.s;  // everything validated: commit (a rejected call leaves the running configuration untouched)
   s.P = P;
   s.use_vloss = P > 1;
   s.tries = P > 1 ? 2 * P : 1;
-  s.sims_bound = p->num_simulations + (P > 1 ? P : 0);
-  if (s.sims_bound + 4 * P + 16 > d.cap) return az_fail(AZ_ERR_CAPACITY, "num_simulations exceeds the engine's node pool (max_simulations)");
+  s.sims_bound = sims_bound;
   s.root_noise = p->root_noise;
   s.deterministic = p->deterministic;
   build_tables(e, p->c_puct_base, p->c_puct_init);
@@ -530,11 +598,15 @@ static int set_search_cfg(az_engine* e, const az_search_params* p) {
 
 extern "C" int az_search_begin(az_engine* e, const int32_t* slots, const int32_t* reuse, int32_t n, const az_search_params* p,
                                int32_t warm_up, const double* noise) {
+  AZ_ENTER(e);
   if (!e) return az_fail(AZ_ERR_BAD_ARG, "null engine");
-  int rc = set_search_cfg(e, p);
-  if (rc) return rc;
+  if (!slots || n < 1 || n > e->E.d.G) return az_fail(AZ_ERR_BAD_ARG, "bad slot list");
+  for (int i = 0; i < n; ++i)
+    if (slots[i] < 0 || slots[i] >= e->E.d.G) return az_fail(AZ_ERR_BAD_ARG, "slot out of range");
   for (int i = 1; i < n; ++i)
     if (slots[i] <= slots[i - 1]) return az_fail(AZ_ERR_BAD_ARG, "az_search_begin: slots must be strictly ascending");
+  int rc = set_search_cfg(e, p);
+  if (rc) return rc;
   rc = upload_slots(e, slots, n);
   if (rc) return rc;
   const AzDims& d = e->E.d;
@@ -579,6 +651,7 @@ static int collect_and_compact(az_engine* e, int32_t tot[2]) {
 }
 
 extern "C" int az_search_select(az_engine* e, int8_t* leaf_obs, int32_t* counts, int32_t* n_leaves, int32_t* n_active) {
+  AZ_ENTER(e);
   if (!e || !n_leaves || !n_active) return az_fail(AZ_ERR_BAD_ARG, "null argument");
   if (e->active.empty()) return az_fail(AZ_ERR_STATE, "az_search_select: no search in progress");
   const AzDims& d = e->E.d;
@@ -601,6 +674,7 @@ extern "C" int az_search_select(az_engine* e, int8_t* leaf_obs, int32_t* counts,
 }
 
 extern "C" int az_search_apply(az_engine* e, const float* priors, const float* values, int32_t n_leaves) {
+  AZ_ENTER(e);
   if (!e) return az_fail(AZ_ERR_BAD_ARG, "null engine");
   if (n_leaves != e->last_total) return az_fail(AZ_ERR_BAD_ARG, "az_search_apply: leaf count does not match the last select");
   const AzDims& d = e->E.d;
@@ -616,6 +690,7 @@ extern "C" int az_search_apply(az_engine* e, const float* priors, const float* v
 }
 
 extern "C" int az_search_run(az_engine* e) {
+  AZ_ENTER(e);
   if (!e) return az_fail(AZ_ERR_BAD_ARG, "null engine");
   if (!e->net || !aznet_ready(e->net)) return az_fail(AZ_ERR_STATE, "az_search_run: network weights not set");
   const AzDims& d = e->E.d;
@@ -635,6 +710,7 @@ extern "C" int az_search_run(az_engine* e) {
 
 extern "C" int az_search_result(az_engine* e, int32_t slot, float* child_N, float* child_W, double* pi, double* root_q,
                                 int32_t* argmax_move) {
+  AZ_ENTER(e);
   int rc = check_slot(e, slot);
   if (rc) return rc;
   const AzDims& d = e->E.d;
@@ -651,6 +727,7 @@ extern "C" int az_search_result(az_engine* e, int32_t slot, float* child_N, floa
 }
 
 extern "C" int az_search_commit(az_engine* e, int32_t slot, int32_t move, double* best_child_q, int32_t* has_next) {
+  AZ_ENTER(e);
   int rc = check_slot(e, slot);
   if (rc) return rc;
   if (move < 0 || move >= e->E.d.A) return az_fail(AZ_ERR_BAD_ARG, "az_search_commit: move out of range");
@@ -664,6 +741,7 @@ extern "C" int az_search_commit(az_engine* e, int32_t slot, int32_t move, double
 
 // ---- device-resident self-play -------------------------------------------------------------------------
 extern "C" int az_selfplay_begin(az_engine* e, const az_selfplay_params* p) {
+  AZ_ENTER(e);
   if (!e || !p) return az_fail(AZ_ERR_BAD_ARG, "null argument");
   if (!e->net || !aznet_ready(e->net)) return az_fail(AZ_ERR_STATE, "az_selfplay_begin: network weights not set");
   int rc = set_search_cfg(e, &p->search);
@@ -685,6 +763,7 @@ extern "C" int az_selfplay_begin(az_engine* e, const az_selfplay_params* p) {
 }
 
 extern "C" int az_selfplay_update(az_engine* e, const az_selfplay_params* p) {
+  AZ_ENTER(e);
   if (!e || !p) return az_fail(AZ_ERR_BAD_ARG, "null argument");
   if (!e->selfplay) return az_fail(AZ_ERR_STATE, "az_selfplay_update: call az_selfplay_begin first");
   if (p->search.c_puct_base > 0.0) {  // new search parameters from the next leaf batch on; searches in flight run to the new bound
@@ -701,6 +780,7 @@ extern "C" int az_selfplay_update(az_engine* e, const az_selfplay_params* p) {
 }
 
 extern "C" int az_selfplay_restart(az_engine* e, const int32_t* slots, int32_t n) {
+  AZ_ENTER(e);
   if (!e) return az_fail(AZ_ERR_BAD_ARG, "null engine");
   if (!e->selfplay) return az_fail(AZ_ERR_STATE, "az_selfplay_restart: call az_selfplay_begin first");
   if (n == 0) return AZ_OK;
@@ -777,6 +857,7 @@ static int selfplay_tick_pipelined(az_engine* e, int n_ticks) {
 }
 
 extern "C" int az_selfplay_tick(az_engine* e, int32_t n_ticks) {
+  AZ_ENTER(e);
   if (!e) return az_fail(AZ_ERR_BAD_ARG, "null engine");
   if (!e->selfplay) return az_fail(AZ_ERR_STATE, "az_selfplay_tick: call az_selfplay_begin first");
   if (e->pipeline && n_ticks > 0) return selfplay_tick_pipelined(e, n_ticks);
@@ -830,9 +911,13 @@ extern "C" int az_selfplay_tick(az_engine* e, int32_t n_ticks) {
   return AZ_OK;
 }
 
-extern "C" int az_sync(az_engine* e) { return e ? rt_sync(e->rt) : az_fail(AZ_ERR_BAD_ARG, "null engine"); }
+extern "C" int az_sync(az_engine* e) {
+  AZ_ENTER(e);
+  return e ? rt_sync(e->rt) : az_fail(AZ_ERR_BAD_ARG, "null engine");
+}
 
 extern "C" int az_get_counters(az_engine* e, az_counters* out) {
+  AZ_ENTER(e);
   if (!e || !out) return az_fail(AZ_ERR_BAD_ARG, "null argument");
   unsigned long long c[CT_COUNT];
   rt_d2h(e->rt, c, e->E.counters, sizeof(c));
@@ -851,8 +936,27 @@ extern "C" int az_get_counters(az_engine* e, az_counters* out) {
   return AZ_OK;
 }
 
+static int drain_impl(az_engine* e, az_game_record* records, int32_t max_games, int32_t* n_games, int8_t* states, float* pis,
+                      float* values, int16_t* moves, int32_t max_samples, int32_t* n_samples, bool dst_on_device);
+
 extern "C" int az_drain_games(az_engine* e, az_game_record* records, int32_t max_games, int32_t* n_games, int8_t* states,
                               float* pis, float* values, int16_t* moves, int32_t max_samples, int32_t* n_samples) {
+  AZ_ENTER(e);
+  return drain_impl(e, records, max_games, n_games, states, pis, values, moves, max_samples, n_samples, false);
+}
+
+extern "C" int az_gather_pack(az_engine* e, az_game_record* records, int32_t max_games, int32_t* n_games, void* d_states, void* d_pis,
+                              void* d_values, int32_t max_samples, int32_t* n_samples) {
+  AZ_ENTER(e);
+  if (!d_states || !d_pis || !d_values) return az_fail(AZ_ERR_BAD_ARG, "az_gather_pack: null device buffer");
+  return drain_impl(e, records, max_games, n_games, (int8_t*)d_states, (float*)d_pis, (float*)d_values, nullptr, max_samples, n_samples, true);
+}
+
+// Finished games leave the sample ring oldest first, as maximal contiguous runs, into host buffers (az_drain_games: DMA to
+// the caller's — ideally pinned — memory) or into caller-owned device buffers (az_gather_pack: the send block of the
+// all-gather, packed device to device).
+static int drain_impl(az_engine* e, az_game_record* records, int32_t max_games, int32_t* n_games, int8_t* states, float* pis,
+                      float* values, int16_t* moves, int32_t max_samples, int32_t* n_samples, bool dst_on_device) {
   if (!e || !n_games || !n_samples) return az_fail(AZ_ERR_BAD_ARG, "null argument");
   const AzDims& d = e->E.d;
   int rc = rt_sync(e->rt);
@@ -878,25 +982,29 @@ extern "C" int az_drain_games(az_engine* e, az_game_record* records, int32_t max
   // game by game.
   unsigned long long run_first = 0;
   int run_len = 0, run_dst = 0;
+  auto cp = [&](void* dst, const void* src, size_t n) {
+    if (dst_on_device) rt_d2d(e->rt, dst, src, n);
+    else rt_d2h_async(e->rt, dst, src, n);
+  };
   auto flush_run = [&]() {
     if (!run_len) return;
     const size_t s0 = (size_t)(run_first % (unsigned long long)d.ring_cap);
     const size_t n1 = std::min((size_t)run_len, (size_t)d.ring_cap - s0), n2 = (size_t)run_len - n1;
     if (states) {
-      rt_d2h_async(e->rt, states + (size_t)run_dst * d.obs_bytes, e->E.r_obs + s0 * d.obs_bytes, n1 * d.obs_bytes);
-      if (n2) rt_d2h_async(e->rt, states + (size_t)(run_dst + n1) * d.obs_bytes, e->E.r_obs, n2 * d.obs_bytes);
+      cp(states + (size_t)run_dst * d.obs_bytes, e->E.r_obs + s0 * d.obs_bytes, n1 * d.obs_bytes);
+      if (n2) cp(states + (size_t)(run_dst + n1) * d.obs_bytes, e->E.r_obs, n2 * d.obs_bytes);
     }
     if (pis) {
-      rt_d2h_async(e->rt, pis + (size_t)run_dst * d.A, e->E.r_pi + s0 * d.A, n1 * d.A * sizeof(float));
-      if (n2) rt_d2h_async(e->rt, pis + (size_t)(run_dst + n1) * d.A, e->E.r_pi, n2 * d.A * sizeof(float));
+      cp(pis + (size_t)run_dst * d.A, e->E.r_pi + s0 * d.A, n1 * d.A * sizeof(float));
+      if (n2) cp(pis + (size_t)(run_dst + n1) * d.A, e->E.r_pi, n2 * d.A * sizeof(float));
     }
     if (values) {
-      rt_d2h_async(e->rt, values + run_dst, e->E.r_z + s0, n1 * sizeof(float));
-      if (n2) rt_d2h_async(e->rt, values + run_dst + n1, e->E.r_z, n2 * sizeof(float));
+      cp(values + run_dst, e->E.r_z + s0, n1 * sizeof(float));
+      if (n2) cp(values + run_dst + n1, e->E.r_z, n2 * sizeof(float));
     }
     if (moves) {
-      rt_d2h_async(e->rt, moves + run_dst, e->E.r_move + s0, n1 * sizeof(int16_t));
-      if (n2) rt_d2h_async(e->rt, moves + run_dst + n1, e->E.r_move, n2 * sizeof(int16_t));
+      cp(moves + run_dst, e->E.r_move + s0, n1 * sizeof(int16_t));
+      if (n2) cp(moves + run_dst + n1, e->E.r_move, n2 * sizeof(int16_t));
     }
     run_len = 0;
   };
@@ -940,27 +1048,41 @@ extern "C" int az_drain_games(az_engine* e, az_game_record* records, int32_t max
   return AZ_OK;
 }
 
-extern "C" int az_sample_ring_device(az_engine* e, void** states, void** pis, void** values, int64_t* head, int32_t* capacity) {
-  if (!e) return az_fail(AZ_ERR_BAD_ARG, "null engine");
-  if (states) *states = e->E.r_obs;
-  if (pis) *pis = e->E.r_pi;
-  if (values) *values = e->E.r_z;
-  if (capacity) *capacity = e->E.d.ring_cap;
-  if (head) {
-    unsigned long long c[CT_COUNT];
-    rt_d2h(e->rt, c, e->E.counters, sizeof(c));
-    *head = (int64_t)c[CT_RING_HEAD];
+extern "C" int az_host_alloc(size_t bytes, void** out) {
+  if (!out) return az_fail(AZ_ERR_BAD_ARG, "null argument");
+#ifndef AZ_EMU
+  void* p = nullptr;
+  cudaError_t ce = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
+  if (ce != cudaSuccess) {
+    cudaGetLastError();
+    return az_fail(AZ_ERR_CUDA, std::string("az_host_alloc: ") + cudaGetErrorString(ce) + " (" + std::to_string(bytes) + " bytes)");
   }
+  *out = p;
+#else
+  *out = malloc(bytes ? bytes : 1);
+  if (!*out) return az_fail(AZ_ERR_CUDA, "az_host_alloc: out of host memory");
+#endif
+  return AZ_OK;
+}
+
+extern "C" int az_host_free(void* p) {
+#ifndef AZ_EMU
+  if (p) cudaFreeHost(p);
+#else
+  free(p);
+#endif
   return AZ_OK;
 }
 
 extern "C" int az_stream(az_engine* e, void** cuda_stream) {
+  AZ_ENTER(e);
   if (!e || !cuda_stream) return az_fail(AZ_ERR_BAD_ARG, "null argument");
   *cuda_stream = (void*)e->rt.stream;
   return AZ_OK;
 }
 
 extern "C" int az_last_net_ms(az_engine* e, float* ms, int32_t* n_evals) {
+  AZ_ENTER(e);
   if (!e || !ms) return az_fail(AZ_ERR_BAD_ARG, "null argument");
 #ifndef AZ_EMU
   cudaEventSynchronize(e->ev1);
@@ -978,6 +1100,7 @@ extern "C" int az_last_net_ms(az_engine* e, float* ms, int32_t* n_evals) {
 }
 
 extern "C" int az_tick_profile(az_engine* e, int32_t enable, double* ms5, int32_t* n_ticks) {
+  AZ_ENTER(e);
   if (!e) return az_fail(AZ_ERR_BAD_ARG, "null engine");
 #ifndef AZ_EMU
   prof_fold(e);
@@ -995,13 +1118,17 @@ extern "C" int az_tick_profile(az_engine* e, int32_t enable, double* ms5, int32_
 // caller-supplied indices (so a numpy RandomState on the host reproduces the reference's minibatches), plus the batch-wide
 // dihedral transformation of utils/transformation.py:160 applied while gathering.
 extern "C" int az_replay_create(az_engine* e, int32_t capacity) {
+  AZ_ENTER(e);
   if (!e || capacity <= 0) return az_fail(AZ_ERR_BAD_ARG, "Expect capacity to be a positive integer");
   if (e->E.rp_obs) return az_fail(AZ_ERR_STATE, "replay already created");
   const AzDims& d = e->E.d;
   e->E.rp_obs = dev_alloc<int8_t>(e, (size_t)capacity * d.obs_bytes);
   e->E.rp_pi = dev_alloc<float>(e, (size_t)capacity * d.A);
   e->E.rp_z = dev_alloc<float>(e, capacity);
-  if (!e->E.rp_z) return az_fail(AZ_ERR_CUDA, "az_replay_create: device allocation failed");
+  if (alloc_check(e, "az_replay_create")) {
+    e->E.rp_obs = nullptr; e->E.rp_pi = nullptr; e->E.rp_z = nullptr;  // whatever was obtained stays in e->allocs and is freed by az_destroy
+    return AZ_ERR_CUDA;
+  }
   e->E.rp_cap = capacity;
   e->rp_samples_added = e->rp_games_added = 0;
   return AZ_OK;
@@ -1028,6 +1155,7 @@ static void replay_copy_in(az_engine* e, const int8_t* so, const float* sp, cons
 }
 
 extern "C" int az_replay_add(az_engine* e, const int8_t* states, const float* pis, const float* values, int32_t n, int32_t n_games) {
+  AZ_ENTER(e);
   if (!e || !e->E.rp_obs) return az_fail(AZ_ERR_STATE, "replay not created");
   if (n < 0 || (n > 0 && (!states || !pis || !values))) return az_fail(AZ_ERR_BAD_ARG, "az_replay_add: bad arguments");
   replay_copy_in(e, states, pis, values, (size_t)n, false);
@@ -1037,6 +1165,7 @@ extern "C" int az_replay_add(az_engine* e, const int8_t* states, const float* pi
 
 // Move every finished, not yet consumed game from the sample ring into the replay, device to device (add_game per game).
 extern "C" int az_replay_ingest(az_engine* e, int32_t* n_games, int32_t* n_samples) {
+  AZ_ENTER(e);
   if (!e || !e->E.rp_obs) return az_fail(AZ_ERR_STATE, "replay not created");
   const AzDims& d = e->E.d;
   int rc = rt_sync(e->rt);
@@ -1067,6 +1196,7 @@ extern "C" int az_replay_ingest(az_engine* e, int32_t* n_games, int32_t* n_sampl
 }
 
 extern "C" int az_replay_info(az_engine* e, int64_t* num_samples_added, int64_t* num_games_added, int32_t* size, int32_t* capacity) {
+  AZ_ENTER(e);
   if (!e || !e->E.rp_obs) return az_fail(AZ_ERR_STATE, "replay not created");
   if (num_samples_added) *num_samples_added = e->rp_samples_added;
   if (num_games_added) *num_games_added = e->rp_games_added;
@@ -1077,6 +1207,7 @@ extern "C" int az_replay_info(az_engine* e, int64_t* num_samples_added, int64_t*
 
 extern "C" int az_replay_sample(az_engine* e, const int32_t* indices, int32_t batch, int32_t transform, int8_t* states, float* pis,
                                 float* values, int32_t outputs_on_device) {
+  AZ_ENTER(e);
   if (!e || !e->E.rp_obs) return az_fail(AZ_ERR_STATE, "replay not created");
   if (!indices || batch <= 0 || !states || !pis || !values) return az_fail(AZ_ERR_BAD_ARG, "az_replay_sample: bad arguments");
   if (transform < 0 || transform > 5) return az_fail(AZ_ERR_BAD_ARG, "az_replay_sample: transform must be in [0, 5]");
@@ -1089,7 +1220,7 @@ extern "C" int az_replay_sample(az_engine* e, const int32_t* indices, int32_t ba
     e->d_rp_obs = dev_alloc<int8_t>(e, (size_t)batch * d.obs_bytes);
     e->d_rp_pi = dev_alloc<float>(e, (size_t)batch * d.A);
     e->d_rp_z = dev_alloc<float>(e, batch);
-    if (!e->d_rp_z) return az_fail(AZ_ERR_CUDA, "az_replay_sample: device allocation failed");
+    if (alloc_check(e, "az_replay_sample")) { e->rp_batch_cap = 0; return AZ_ERR_CUDA; }
     e->rp_batch_cap = batch;
   }
   rt_h2d(e->rt, e->d_rp_idx, indices, (size_t)batch * sizeof(int32_t));

@@ -115,7 +115,10 @@ static void dev_set(AzRt& rt, std::vector<void*>& allocs, float*& slot, const st
 AzNet* aznet_create(const AzDims& d, const az_config& cfg, AzRt& rt, int max_leaves, std::string& err) {
   AzNet* n = new AzNet();
   n->blocks = cfg.num_res_blocks;
-  n->C = cfg.num_filters;
+  // the towers run on a channel count padded to their tile granularity (the reference's default Gomoku net has 40 filters,
+  // training_gomoku.py:38): padded channels carry zero weights and zero bias, so they stay exactly zero through every layer
+  n->C_src = cfg.num_filters;
+  n->C = (cfg.num_filters + (cfg.net_precision == AZ_NET_FP32 ? 15 : 63)) / (cfg.net_precision == AZ_NET_FP32 ? 16 : 64) * (cfg.net_precision == AZ_NET_FP32 ? 16 : 64);
   n->fc = cfg.num_fc_units;
   n->A = d.A;
   n->precision = cfg.net_precision;
@@ -131,20 +134,27 @@ AzNet* aznet_create(const AzDims& d, const az_config& cfg, AzRt& rt, int max_lea
   g.RP = g.Wr * g.Wr;
   g.guard = ((g.Wr + 1 + 127) / 128) * 128;  // >= one board row + 1, and a whole number of 128-row tiles
   g.cin_pad = 32;
-  if (n->C % 64 != 0 && n->precision == AZ_NET_BF16) { err = "bf16 tower needs num_filters to be a multiple of 64"; delete n; return nullptr; }
-  if (n->C % 16 != 0 || n->C < 16) { err = "num_filters must be a multiple of 16"; delete n; return nullptr; }
+  g.in_dup = 0;
+  if (n->precision != AZ_NET_FP32 && n->precision != AZ_NET_BF16 && n->precision != AZ_NET_BF16X3) { err = "unknown net_precision"; delete n; return nullptr; }
+  if (cfg.num_filters < 1 || cfg.num_fc_units < 1 || cfg.num_res_blocks < 0) { err = "bad network dimensions"; delete n; return nullptr; }
   if (d.planes > g.cin_pad) { err = "observation has more than 32 planes"; delete n; return nullptr; }
   n->rows_total = (size_t)max_leaves * g.RP + 2 * (size_t)g.guard + 1024;
-  const size_t esz = n->precision == AZ_NET_BF16 ? 2 : 4;
+  const size_t esz = aznet_is_tc(n) ? 2 : 4;
+  const size_t cw = (size_t)(n->precision == AZ_NET_BF16X3 ? 3 * n->C : n->C);  // split rows: [hi | lo | hi]
   n->act_in = rt_alloc(n->rows_total * g.cin_pad * esz);
-  n->act_x = rt_alloc(n->rows_total * n->C * esz);
-  n->act_mid = rt_alloc(n->rows_total * n->C * esz);
-  if (!n->act_in || !n->act_x || !n->act_mid) { err = "activation buffers: out of device memory"; aznet_destroy(n); return nullptr; }
-  // 2*MAC per evaluation, for the roofline
-  const double hw = (double)g.Hc * g.Hc;
-  n->flops = 2.0 * hw * 9.0 * d.planes * n->C + (double)n->blocks * 2.0 * (2.0 * hw * 9.0 * n->C * n->C) + 2.0 * hw * n->C * 3.0 +
+  n->act_x = rt_alloc(n->rows_total * cw * esz);
+  n->act_mid = rt_alloc(n->rows_total * cw * esz);
+  n->dbg_count = (int32_t*)rt_alloc(sizeof(int32_t));
+  if (!n->act_in || !n->act_x || !n->act_mid || !n->dbg_count) {
+    err = "activation buffers: out of device memory (" + std::to_string((n->rows_total * (g.cin_pad + 2 * cw) * esz) >> 20) + " MB)";
+    aznet_destroy(n);
+    return nullptr;
+  }
+  // 2*MAC per evaluation, for the roofline: the network's own channel count, not the padded one
+  const double hw = (double)g.Hc * g.Hc, cs = (double)n->C_src;
+  n->flops = 2.0 * hw * 9.0 * d.planes * cs + (double)n->blocks * 2.0 * (2.0 * hw * 9.0 * cs * cs) + 2.0 * hw * cs * 3.0 +
              2.0 * (2.0 * hw) * d.A + 2.0 * hw * n->fc + 2.0 * n->fc;
-  if (n->precision == AZ_NET_BF16) {
+  if (aznet_is_tc(n)) {
     if (aznet_tc_create(n, rt, err)) { aznet_destroy(n); return nullptr; }
   }
   return n;
@@ -156,11 +166,14 @@ void aznet_destroy(AzNet* n) {
   rt_free(n->act_in);
   rt_free(n->act_x);
   rt_free(n->act_mid);
+  rt_free(n->dbg_count);
   for (void* p : n->allocs) rt_free(p);
   delete n;
 }
 
 double aznet_flops_per_eval(const AzNet* n) { return n ? n->flops : 0.0; }
+int aznet_padded_filters(const AzNet* n) { return n ? n->C : 0; }
+int aznet_tc_mode_of(const AzNet* n) { return n && aznet_is_tc(n) ? aznet_tc_mode(n) : -1; }
 int aznet_ready(const AzNet* n) { return n && n->ready; }
 
 // Fold conv(no bias)+BN into tap-major weights [9][cin_pad][cout] and a bias vector.
@@ -177,23 +190,23 @@ static void fold_conv3(const float* w, const float* gm, const float* bt, const f
 }
 
 int aznet_set_weights(AzNet* n, AzRt& rt, const float* const* T, const int64_t* numel, int nt, std::string& err) {
-  const int C = n->C, nb = n->blocks, fc = n->fc, A = n->A;
+  const int C = n->C, Cs = n->C_src, nb = n->blocks, fc = n->fc, A = n->A;
   const int planes = n->g.planes, HW = n->g.Hc * n->g.Hc;
   const int expect = 21 + 10 * nb;
   if (nt != expect) { err = "expected " + std::to_string(expect) + " tensors (state_dict without num_batches_tracked), got " + std::to_string(nt); return AZ_ERR_BAD_ARG; }
   std::vector<int64_t> want;
-  want.push_back((int64_t)C * planes * 9);
-  for (int k = 0; k < 4; ++k) want.push_back(C);
+  want.push_back((int64_t)Cs * planes * 9);
+  for (int k = 0; k < 4; ++k) want.push_back(Cs);
   for (int b = 0; b < nb; ++b)
     for (int h = 0; h < 2; ++h) {
-      want.push_back((int64_t)C * C * 9);
-      for (int k = 0; k < 4; ++k) want.push_back(C);
+      want.push_back((int64_t)Cs * Cs * 9);
+      for (int k = 0; k < 4; ++k) want.push_back(Cs);
     }
-  want.push_back(2 * C);
+  want.push_back(2 * Cs);
   for (int k = 0; k < 4; ++k) want.push_back(2);
   want.push_back((int64_t)A * 2 * HW);
   want.push_back(A);
-  want.push_back(C);
+  want.push_back(Cs);
   for (int k = 0; k < 4; ++k) want.push_back(1);
   want.push_back((int64_t)fc * HW);
   want.push_back(fc);
@@ -205,6 +218,41 @@ int aznet_set_weights(AzNet* n, AzRt& rt, const float* const* T, const int64_t* 
             " (AlphaZeroNet geometry mismatch)";
       return AZ_ERR_BAD_ARG;
     }
+  // channel padding (C_src -> C): zero weight rows / columns, BN of the padded channels = identity with zero shift
+  std::vector<std::vector<float>> padded;
+  std::vector<const float*> Tp;
+  if (C != Cs) {
+    padded.resize(nt);
+    Tp.assign(T, T + nt);
+    auto pad_conv = [&](int i, int cout_s, int cin_s, int cout_p, int cin_p, int taps) {
+      padded[i].assign((size_t)cout_p * cin_p * taps, 0.f);
+      for (int co = 0; co < cout_s; ++co)
+        for (int ci = 0; ci < cin_s; ++ci)
+          memcpy(&padded[i][((size_t)co * cin_p + ci) * taps], T[i] + ((size_t)co * cin_s + ci) * taps, taps * sizeof(float));
+      Tp[i] = padded[i].data();
+    };
+    auto pad_bn = [&](int i0) {  // gamma, beta, running_mean, running_var
+      const float fill[4] = {1.f, 0.f, 0.f, 1.f};
+      for (int k = 0; k < 4; ++k) {
+        padded[i0 + k].assign(C, fill[k]);
+        memcpy(padded[i0 + k].data(), T[i0 + k], Cs * sizeof(float));
+        Tp[i0 + k] = padded[i0 + k].data();
+      }
+    };
+    int i = 0;
+    pad_conv(i, Cs, planes, C, planes, 9);
+    pad_bn(i + 1);
+    i += 5;
+    for (int b = 0; b < 2 * nb; ++b) {
+      pad_conv(i, Cs, Cs, C, C, 9);
+      pad_bn(i + 1);
+      i += 5;
+    }
+    pad_conv(i, 2, Cs, 2, C, 1);  // policy head 1x1 conv
+    i += 7;
+    pad_conv(i, 1, Cs, 1, C, 1);  // value head 1x1 conv
+    T = Tp.data();
+  }
   // device buffers are allocated on the first call and refreshed in place afterwards (checkpoint hot-swap path)
   const int n_conv = 1 + 2 * nb;
   if ((int)n->conv_w.size() != n_conv) {
@@ -275,7 +323,7 @@ int aznet_set_weights(AzNet* n, AzRt& rt, const float* const* T, const int64_t* 
   hp.pol_fc_wT = n->head_dev[4]; hp.val_fc1_wT = n->head_dev[5]; hp.val_w = n->head_dev[6]; hp.val_b = n->head_dev[7];
   hp.val_fc1_w = n->head_dev[8]; hp.val_fc1_b = n->head_dev[9]; hp.val_fc2_w = n->head_dev[10]; hp.val_fc2_b = n->head_dev[11];
   if (!hp.val_fc2_b) { err = "out of device memory"; return AZ_ERR_CUDA; }
-  if (n->precision == AZ_NET_BF16) {
+  if (aznet_is_tc(n)) {
     int rc = aznet_tc_set_weights(n, rt, err);
     if (rc) return rc;
   }
@@ -288,7 +336,7 @@ int aznet_forward(AzNet* n, AzRt& rt, const int8_t* obs_base, const int32_t* row
   if (!n || !n->ready) return AZ_ERR_STATE;
   if (max_rows > n->max_leaves) max_rows = n->max_leaves;
   const NetGeom& g = n->g;
-  if (n->precision == AZ_NET_BF16) return aznet_tc_forward(n, rt, obs_base, row_list, n_rows_dev, max_rows, priors_base, values_base, pri_stride);
+  if (aznet_is_tc(n)) return aznet_tc_forward(n, rt, obs_base, row_list, n_rows_dev, max_rows, priors_base, values_base, pri_stride);
   {
     long long work = (long long)max_rows * g.nc;
     int blocks = (int)std::min<long long>((work + 255) / 256, 148 * 8);
@@ -306,10 +354,108 @@ int aznet_forward(AzNet* n, AzRt& rt, const int8_t* obs_base, const int32_t* row
     k_conv_f32<<<grid, 256, 0, rt.stream>>>(MID, n->conv_w[2 + 2 * b], n->conv_b[2 + 2 * b], X, X, n_rows_dev, g, n->C, n->C, 1);
     rt.launches += 2;
   }
-  launch_heads<float>(rt.stream, X, row_list, n_rows_dev, n->hp, g, n->C, n->A, n->fc, priors_base, values_base, pri_stride, max_rows);
+  launch_heads<float>(rt.stream, X, row_list, n_rows_dev, n->hp, g, n->C, n->C, 0, n->A, n->fc, priors_base, values_base, pri_stride, max_rows);
   rt.launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_az_error = std::string("network launch: ") + cudaGetErrorString(e); return AZ_ERR_CUDA; }
   return AZ_OK;
 }
 
+
+// ---- one conv layer on caller-supplied activations (tests: the benched kernel against a plain convolution) ----------------
+// in: float [cnt][cin][Hc][Hc] on the canvas the tower runs on (cin = observation planes for layer 0, num_filters otherwise),
+// res: float [cnt][num_filters][Hc][Hc] or null, out: float [cnt][num_filters][Hc][Hc].  Values are converted to the tower's
+// storage type on the way in (bf16 rounding; hi + lo for the split tower) and back to float on the way out.
+int aznet_debug_layer(AzNet* n, AzRt& rt, int li, const float* in, const float* res, int cnt, float* out, std::string& err) {
+  if (!n || !n->ready) { err = "network weights not set"; return AZ_ERR_STATE; }
+  const int n_conv = 1 + 2 * n->blocks;
+  if (li < 0 || li >= n_conv) { err = "layer index out of range"; return AZ_ERR_BAD_ARG; }
+  if (cnt < 1 || cnt > n->max_leaves) { err = "leaf count out of range"; return AZ_ERR_BAD_ARG; }
+  if (res && (li < 2 || (li & 1))) { err = "only the second conv of a block takes a residual"; return AZ_ERR_BAD_ARG; }
+  const NetGeom& g = n->g;
+  const bool tc = aznet_is_tc(n), split = n->precision == AZ_NET_BF16X3;
+  const int C = n->C, Cs = n->C_src, Hc = g.Hc;
+  const int cin_src = li == 0 ? g.planes : Cs;
+  const size_t rows = (size_t)2 * g.guard + (size_t)cnt * g.RP;
+  const size_t esz = tc ? 2 : 4;
+  const size_t w_in = li == 0 ? (size_t)(tc ? 64 : g.cin_pad) : (size_t)(split ? 3 * C : C);
+  const size_t w_act = (size_t)(split ? 3 * C : C);
+  auto put = [&](std::vector<unsigned char>& buf, size_t width, size_t row, int c, float v, bool first_layer) {
+    if (!tc) { ((float*)buf.data())[row * width + c] = v; return; }
+    __nv_bfloat16* b = (__nv_bfloat16*)buf.data() + row * width;
+    const __nv_bfloat16 hi = __float2bfloat16(v);
+    b[c] = hi;
+    if (split) {
+      if (first_layer) b[32 + c] = hi;
+      else { b[C + c] = __float2bfloat16(v - __bfloat162float(hi)); b[2 * C + c] = hi; }
+    }
+  };
+  auto pack = [&](const float* src, int ch, size_t width, bool first_layer) {
+    std::vector<unsigned char> buf(rows * width * esz, 0);
+    for (int l = 0; l < cnt; ++l)
+      for (int c = 0; c < ch; ++c)
+        for (int y = 0; y < Hc; ++y)
+          for (int x = 0; x < Hc; ++x)
+            put(buf, width, (size_t)g.guard + (size_t)l * g.RP + (size_t)y * g.Wr + x, c, src[(((size_t)l * ch + c) * Hc + y) * Hc + x], first_layer);
+    return buf;
+  };
+  void* d_in = li == 0 ? n->act_in : ((li & 1) ? n->act_x : n->act_mid);
+  void* d_out = (li & 1) ? n->act_mid : n->act_x;
+  {
+    std::vector<unsigned char> b = pack(in, cin_src, w_in, li == 0);
+    rt_h2d(rt, d_in, b.data(), b.size());
+  }
+  if (res) {
+    std::vector<unsigned char> b = pack(res, Cs, w_act, false);
+    rt_h2d(rt, n->act_x, b.data(), b.size());
+  } else if (d_out != d_in) {
+    rt_zero(rt, d_out, rows * w_act * esz);
+  }
+  int32_t c32 = cnt;
+  rt_h2d(rt, n->dbg_count, &c32, sizeof(c32));
+  if (tc) {
+    int rc = aznet_tc_layer(n, rt, li, res != nullptr, n->dbg_count, cnt);
+    if (rc) return rc;
+  } else {
+    const long long Mmax = (long long)cnt * g.RP;
+    dim3 grid((unsigned)((Mmax + 63) / 64), (unsigned)((C + 63) / 64));
+    k_conv_f32<<<grid, 256, 0, rt.stream>>>((const float*)d_in, n->conv_w[li], n->conv_b[li], res ? (const float*)n->act_x : nullptr, (float*)d_out,
+                                            n->dbg_count, g, li == 0 ? g.cin_pad : C, C, 1);
+    rt.launches++;
+  }
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) { err = std::string("layer launch: ") + cudaGetErrorString(ce); return AZ_ERR_CUDA; }
+  std::vector<unsigned char> ob(rows * w_act * esz);
+  rt_d2h(rt, ob.data(), d_out, ob.size());
+  if (rt_sync(rt)) { err = g_az_error; return AZ_ERR_CUDA; }
+  for (int l = 0; l < cnt; ++l)
+    for (int c = 0; c < Cs; ++c)
+      for (int y = 0; y < Hc; ++y)
+        for (int x = 0; x < Hc; ++x) {
+          const size_t row = (size_t)g.guard + (size_t)l * g.RP + (size_t)y * g.Wr + x;
+          float v;
+          if (!tc) v = ((const float*)ob.data())[row * w_act + c];
+          else {
+            const __nv_bfloat16* b = (const __nv_bfloat16*)ob.data() + row * w_act;
+            v = __bfloat162float(b[c]);
+            if (split) v += __bfloat162float(b[C + c]);
+          }
+          out[(((size_t)l * Cs + c) * Hc + y) * Hc + x] = v;
+        }
+  // the padding the next layer relies on must have survived: zero board rows / separator cells, and (split) hi copies equal
+  for (int l = 0; l < cnt; ++l)
+    for (int r = 0; r < g.RP; ++r) {
+      const int y = r / g.Wr, x = r - y * g.Wr;
+      const bool pad_cell = y >= Hc || x >= Hc;
+      const size_t row = (size_t)g.guard + (size_t)l * g.RP + r;
+      for (size_t c = 0; c < w_act; ++c) {
+        float v = tc ? __bfloat162float(((const __nv_bfloat16*)ob.data())[row * w_act + c]) : ((const float*)ob.data())[row * w_act + c];
+        if (pad_cell && v != 0.f) { err = "padding row written: leaf " + std::to_string(l) + " row " + std::to_string(r); return AZ_ERR_STATE; }
+        if (!pad_cell && split && c < (size_t)C && v != __bfloat162float(((const __nv_bfloat16*)ob.data())[row * w_act + 2 * C + c])) {
+          err = "split row: hi copies differ";
+          return AZ_ERR_STATE;
+        }
+      }
+    }
+  return AZ_OK;
+}

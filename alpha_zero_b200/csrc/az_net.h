@@ -21,5 +21,8 @@ int aznet_set_weights(AzNet* n, AzRt& rt, const float* const* tensors, const int
 // for i < *n_rows_dev (device-side count, <= max_rows).
 int aznet_forward(AzNet* n, AzRt& rt, const int8_t* obs_base, const int32_t* row_list, const int32_t* n_rows_dev, int max_rows,
                   float* priors_base, float* values_base, int pri_stride);
+int aznet_debug_layer(AzNet* n, AzRt& rt, int li, const float* in, const float* res, int cnt, float* out, std::string& err);
+int aznet_tc_mode_of(const AzNet* n);
+int aznet_padded_filters(const AzNet* n);
 double aznet_flops_per_eval(const AzNet* n);
 int aznet_ready(const AzNet* n);

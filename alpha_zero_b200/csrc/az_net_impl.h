@@ -17,6 +17,7 @@ struct NetGeom {
   int RP;                        // rows per leaf = (Hc+1)*(Hc+1)
   int guard;                     // zero rows before the first and after the last leaf
   int cin_pad;                   // channels of the input feature rows (>= planes)
+  int in_dup;                    // 1: input rows carry the planes twice (channels 0.. and 32..), split-bf16 tower
 };
 
 struct HeadParams {
@@ -28,7 +29,8 @@ struct HeadParams {
 struct AzNetTc;  // tensor-core tower state (az_net_tc.cu)
 
 struct AzNet {
-  int blocks = 0, C = 0, fc = 0, A = 0, precision = 0, max_leaves = 0, ready = 0;
+  int blocks = 0, C = 0, C_src = 0, fc = 0, A = 0, precision = 0, max_leaves = 0, ready = 0;  // C: padded channel count the towers run on
+  int32_t* dbg_count = nullptr;
   NetGeom g;
   size_t rows_total = 0;
   void *act_in = nullptr, *act_x = nullptr, *act_mid = nullptr;
@@ -48,3 +50,6 @@ void aznet_tc_destroy(AzNet* n);
 int aznet_tc_set_weights(AzNet* n, AzRt& rt, std::string& err);
 int aznet_tc_forward(AzNet* n, AzRt& rt, const int8_t* obs_base, const int32_t* row_list, const int32_t* n_rows_dev, int max_rows,
                      float* priors_base, float* values_base, int pri_stride);
+int aznet_tc_layer(AzNet* n, AzRt& rt, int li, bool with_res, const int32_t* n_rows_dev, int max_rows);
+int aznet_tc_mode(const AzNet* n);
+static inline bool aznet_is_tc(const AzNet* n) { return n->precision == AZ_NET_BF16 || n->precision == AZ_NET_BF16X3; }

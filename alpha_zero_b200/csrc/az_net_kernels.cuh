@@ -25,7 +25,8 @@ static __global__ void k_net_input(const int8_t* __restrict__ obs_base, const in
     const int nvec = (int)(g.cin_pad * sizeof(T) / 16);
 #pragma unroll
     for (int k = 0; k < kData; ++k) d4[k] = s4[k];
-    for (int k = kData; k < nvec; ++k) d4[k] = make_uint4(0, 0, 0, 0);
+    // in_dup (split-bf16 tower): channels 32..63 repeat the planes, the layer multiplies them with the low weight terms
+    for (int k = kData; k < nvec; ++k) d4[k] = (g.in_dup && k < 2 * kData) ? s4[k - kData] : make_uint4(0, 0, 0, 0);
   }
 }
 
@@ -40,8 +41,9 @@ __device__ __forceinline__ float head_ld(const T* p) { return (float)*p; }
 
 template <typename T, int LPB>
 static __global__ void __launch_bounds__(256) k_heads(const T* __restrict__ feat, const int32_t* __restrict__ row_list,
-                                                      const int32_t* __restrict__ n_rows, HeadParams hp, NetGeom g, int C, int A,
-                                                      int fc, float* __restrict__ priors, float* __restrict__ values, int pri_stride) {
+                                                      const int32_t* __restrict__ n_rows, HeadParams hp, NetGeom g, int C, int fstride,
+                                                      int split, int A, int fc, float* __restrict__ priors, float* __restrict__ values,
+                                                      int pri_stride) {
   const int n = *n_rows;
   const int leaf0 = blockIdx.x * LPB;
   if (leaf0 >= n) return;
@@ -57,17 +59,20 @@ static __global__ void __launch_bounds__(256) k_heads(const T* __restrict__ feat
   for (int idx = tid; idx < nl * HW; idx += 256) {
     const int l = idx / HW, pos = idx - l * HW;
     const int y = pos / g.Hc, x = pos - y * g.Hc;
-    const T* f = feat + ((size_t)g.guard + (size_t)(leaf0 + l) * g.RP + (size_t)y * g.Wr + x) * C;
+    // a feature row holds `fstride` elements; split rows are [hi(C) | lo(C) | hi(C)] and the value of a channel is hi + lo
+    const T* f = feat + ((size_t)g.guard + (size_t)(leaf0 + l) * g.RP + (size_t)y * g.Wr + x) * fstride;
     float p0 = 0.f, p1 = 0.f, v0 = 0.f;
     if (sizeof(T) == 2) {
       const uint4* f4 = reinterpret_cast<const uint4*>(f);
-      for (int c8 = 0; c8 < C / 8; ++c8) {
+      const int nchunk = (split ? 2 * C : C) / 8;
+      for (int c8 = 0; c8 < nchunk; ++c8) {
         const uint4 raw = f4[c8];
         const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+        const int cb = c8 * 8 >= C ? c8 * 8 - C : c8 * 8;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float a0 = __uint_as_float(w[k] << 16), a1 = __uint_as_float(w[k] & 0xffff0000u);
-          const int c = c8 * 8 + k * 2;
+          const int c = cb + k * 2;
           p0 = fmaf(a0, s_w[c], fmaf(a1, s_w[c + 1], p0));
           p1 = fmaf(a0, s_w[C + c], fmaf(a1, s_w[C + c + 1], p1));
           v0 = fmaf(a0, s_w[2 * C + c], fmaf(a1, s_w[2 * C + c + 1], v0));
@@ -138,14 +143,15 @@ static __global__ void __launch_bounds__(256) k_heads(const T* __restrict__ feat
 // host helper: launch the heads with the largest LPB whose shared memory fits the default 48 KB
 template <typename T>
 static inline void launch_heads(cudaStream_t stream, const T* feat, const int32_t* row_list, const int32_t* n_rows, const HeadParams& hp,
-                                const NetGeom& g, int C, int A, int fc, float* priors, float* values, int pri_stride, int max_rows) {
+                                const NetGeom& g, int C, int fstride, int split, int A, int fc, float* priors, float* values, int pri_stride,
+                                int max_rows) {
   const int HW = g.Hc * g.Hc;
   const size_t per = (size_t)(3 * HW + fc + A) * sizeof(float);
   const size_t wsm = (size_t)3 * C * sizeof(float);
   if (per * 8 + wsm <= 48 * 1024)
-    k_heads<T, 8><<<(max_rows + 7) / 8, 256, per * 8 + wsm, stream>>>(feat, row_list, n_rows, hp, g, C, A, fc, priors, values, pri_stride);
+    k_heads<T, 8><<<(max_rows + 7) / 8, 256, per * 8 + wsm, stream>>>(feat, row_list, n_rows, hp, g, C, fstride, split, A, fc, priors, values, pri_stride);
   else if (per * 4 + wsm <= 48 * 1024)
-    k_heads<T, 4><<<(max_rows + 3) / 4, 256, per * 4 + wsm, stream>>>(feat, row_list, n_rows, hp, g, C, A, fc, priors, values, pri_stride);
+    k_heads<T, 4><<<(max_rows + 3) / 4, 256, per * 4 + wsm, stream>>>(feat, row_list, n_rows, hp, g, C, fstride, split, A, fc, priors, values, pri_stride);
   else
-    k_heads<T, 1><<<max_rows, 256, per + wsm, stream>>>(feat, row_list, n_rows, hp, g, C, A, fc, priors, values, pri_stride);
+    k_heads<T, 1><<<max_rows, 256, per + wsm, stream>>>(feat, row_list, n_rows, hp, g, C, fstride, split, A, fc, priors, values, pri_stride);
 }

@@ -33,6 +33,7 @@
 struct AzNetTc {
   CUtensorMap map_in, map_x, map_mid;
   CUtensorMap hmap_in[2], hmap_x[2], hmap_mid[2];  // halo kernel: [0] 256-row box, [1] tail box (AR-256 rows)
+  int split = 0;           // AZ_NET_BF16X3: activation rows [hi | lo | hi] (3 C channels), weights [W_hi | W_hi | W_lo]
   int mode = 0;            // AZ_TC_MODE: 0 = one TMA box per tap, 1/2 = halo tile + row-shifted descriptors (base-offset variants)
   int halo = 0, AR = 0;
   int res_l2 = 0;
@@ -662,6 +663,7 @@ struct XLayer {
   int sub_bytes;   // bytes of one TMA box = NBR * Hc * 128
   int sub_stride;  // the same rounded up to 1024 (swizzle atom alignment of the next slot)
   int bstages;     // weight ring depth: X_BSTAGES for a pair (half chunks), half of it for a single CTA (same bytes)
+  int ostride;     // elements per activation row of `out` / `res`: cout, or 3 * cout for the split-bf16 rows [hi | lo | hi]
 };
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
@@ -677,7 +679,11 @@ __device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* m
                : "memory");
 }
 
-template <bool PAIR>
+// SPLIT (AZ_NET_BF16X3): every fp32 value travels as two bf16 terms, value = hi + lo (16 significand bits).  Activation rows
+// are [hi(C) | lo(C) | hi(C)] and the weights of a layer are packed [W_hi | W_hi | W_lo] along K, so the unchanged main loop
+// accumulates a_hi*w_hi + a_lo*w_hi + a_hi*w_lo in fp32 (the dropped a_lo*w_lo term is 2^-16 relative): 3x the MMAs of the
+// bf16 tower, ~2^-16 instead of 2^-8 relative error per layer.  Only the epilogue differs: it splits its fp32 result again.
+template <bool PAIR, bool SPLIT>
 __global__ void __launch_bounds__(H_THREADS, 1)
 k_conv_tc_x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const float* __restrict__ bias,
             const __nv_bfloat16* res, __nv_bfloat16* out, const int32_t* __restrict__ n_rows, XLayer L) {
@@ -851,7 +857,7 @@ k_conv_tc_x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     int it = 0;
     const int tstep = PAIR ? 2 * ustep : ustep;
     const int t_first = PAIR ? 2 * unit0 + (int)crank : unit0;
-    if (L.has_res && unit0 < num_units) prefetch((long long)t_first * L.TH, q * 32, col0);
+    if (!SPLIT && L.has_res && unit0 < num_units) prefetch((long long)t_first * L.TH, q * 32, col0);
     for (int u = unit0; u < num_units; u += ustep, ++it) {
       const int t = PAIR ? 2 * u + (int)crank : u;
       const long long tile_row0 = (long long)t * L.TH;
@@ -863,6 +869,45 @@ k_conv_tc_x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         const int h = ps / npass_c, pc = ps - h * npass_c;
         const int cc = col0 + pc * 32;
         const int l0 = h * 128 + q * 32;
+        if constexpr (SPLIT) {
+          // every lane owns one row: 64-byte segments of the hi / lo / hi column groups, read and written directly
+          const int l = l0 + lane;
+          const long long m = tile_row0 + l;
+          const int r = (int)(m % L.RP);
+          const bool inb = (l < L.TH) && (m < M);
+          const bool valid = inb && (r / L.Hc) < L.Hc;
+          const size_t grow = ((size_t)L.guard + (size_t)(inb ? m : 0)) * L.ostride + cc;
+          __align__(16) __nv_bfloat16 rh[32], rl[32];
+          if (L.has_res && valid) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              reinterpret_cast<uint4*>(rh)[k] = reinterpret_cast<const uint4*>(res + grow)[k];
+              reinterpret_cast<uint4*>(rl)[k] = reinterpret_cast<const uint4*>(res + grow + L.cout)[k];
+            }
+          }
+          uint32_t v[32];
+          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * 2 + h) * L.cout + cc), v);
+          if (inb) {
+            __align__(16) __nv_bfloat16 oh[32], ol[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float f = __uint_as_float(v[j]) + s_bias[cc + j];
+              if (L.has_res && valid) f += __bfloat162float(rh[j]) + __bfloat162float(rl[j]);
+              if (L.relu) f = fmaxf(f, 0.f);
+              if (!valid) f = 0.f;
+              const __nv_bfloat16 hb = __float2bfloat16(f);
+              oh[j] = hb;
+              ol[j] = __float2bfloat16(f - __bfloat162float(hb));
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              reinterpret_cast<uint4*>(out + grow)[k] = reinterpret_cast<const uint4*>(oh)[k];
+              reinterpret_cast<uint4*>(out + grow + L.cout)[k] = reinterpret_cast<const uint4*>(ol)[k];
+              reinterpret_cast<uint4*>(out + grow + 2 * L.cout)[k] = reinterpret_cast<const uint4*>(oh)[k];
+            }
+          }
+          continue;
+        }
         uint32_t v[32];
         tc_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * 2 + h) * L.cout + cc), v);
         if (L.has_res) {
@@ -984,10 +1029,12 @@ int aznet_tc_create(AzNet* n, AzRt& rt, std::string& err) {
   rt_free(n->act_in);
   n->act_in = rt_alloc(n->rows_total * 64 * 2);
   if (!n->act_in) { err = "out of device memory"; return AZ_ERR_CUDA; }
-  if (n->C != 64 && n->C != 128 && n->C != 256) { err = "bf16 tower supports num_filters 64, 128 or 256"; return AZ_ERR_BAD_ARG; }
+  if (n->C != 64 && n->C != 128 && n->C != 256) { err = "tensor-core towers support num_filters <= 128 (padded to 64 / 128) or 193..256 (padded to 256)"; return AZ_ERR_BAD_ARG; }
+  tc->split = n->precision == AZ_NET_BF16X3;
+  const uint64_t CW = (uint64_t)(tc->split ? 3 * n->C : n->C);  // channels of a stored activation row
   int rc = make_map(&tc->map_in, n->act_in, 64, n->rows_total, TC_BM, err);
-  if (!rc) rc = make_map(&tc->map_x, n->act_x, n->C, n->rows_total, TC_BM, err);
-  if (!rc) rc = make_map(&tc->map_mid, n->act_mid, n->C, n->rows_total, TC_BM, err);
+  if (!rc) rc = make_map(&tc->map_x, n->act_x, CW, n->rows_total, TC_BM, err);
+  if (!rc) rc = make_map(&tc->map_mid, n->act_mid, CW, n->rows_total, TC_BM, err);
   if (rc) return rc;
   tc->smem_bytes = (size_t)TC_STAGES * (TC_BM * TC_BK * 2 + (size_t)n->C * TC_BK * 2) + 1024 + 256;
   cudaError_t e = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc->smem_bytes);
@@ -1002,6 +1049,7 @@ int aznet_tc_create(AzNet* n, AzRt& rt, std::string& err) {
   // 0 = one TMA box per tap
   tc->mode = md ? atoi(md) : AZ_TC_MODE_DEFAULT;
   if (n->C > 128) tc->mode = 0;  // the halo tile of a 256-channel layer does not fit next to the weight ring
+  if (tc->split && tc->mode != 5 && tc->mode != 6) { err = "bf16x3 tower runs on the dense-x kernel only (num_filters <= 128, AZ_TC_MODE 5 or 6)"; return AZ_ERR_BAD_ARG; }
   if (tc->mode == 5 || tc->mode == 6) {
     // dense-x layout: rows y*Hc + x, one zero board row per leaf, no separator column.  The input and head kernels follow
     // NetGeom, so only the geometry changes for them.  6 = the single-CTA build of the same kernel.  A canvas too wide for the
@@ -1013,6 +1061,7 @@ int aznet_tc_create(AzNet* n, AzRt& rt, std::string& err) {
     const size_t x_smem = (size_t)X_ASLOTS * sub_stride + (size_t)X_BSTAGES * (n->C / 2) * TC_BK * 2 + (size_t)H_EPI_WARPS * 32 * 80 + (size_t)n->C * 4 +
                           (size_t)(2 * X_ASLOTS + 2 * X_BSTAGES + 4) * 8 + 16 + 1024;
     if (x_smem > 227 * 1024) {
+      if (tc->split) { err = "bf16x3 tower: the dense-x ring does not fit this canvas"; return AZ_ERR_BAD_ARG; }
       tc->mode = 4;
     } else {
       NetGeom& g = n->g;
@@ -1025,11 +1074,14 @@ int aznet_tc_create(AzNet* n, AzRt& rt, std::string& err) {
       tc->x_smem = x_smem;
       const uint64_t board_rows = n->rows_total / (uint64_t)Hc;
       rc = make_map_3d(&tc->xmap_in, n->act_in, 64, Hc, board_rows, nbr, err);
-      if (!rc) rc = make_map_3d(&tc->xmap_x, n->act_x, n->C, Hc, board_rows, nbr, err);
-      if (!rc) rc = make_map_3d(&tc->xmap_mid, n->act_mid, n->C, Hc, board_rows, nbr, err);
+      if (!rc) rc = make_map_3d(&tc->xmap_x, n->act_x, CW, Hc, board_rows, nbr, err);
+      if (!rc) rc = make_map_3d(&tc->xmap_mid, n->act_mid, CW, Hc, board_rows, nbr, err);
       if (rc) return rc;
-      e = cudaFuncSetAttribute(k_conv_tc_x<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc->x_smem);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_tc_x<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc->x_smem);
+      g.in_dup = tc->split;  // layer 0 of the split tower reads the planes twice: [x | x] against [W_hi | W_lo]
+      e = cudaFuncSetAttribute(k_conv_tc_x<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc->x_smem);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_tc_x<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc->x_smem);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_tc_x<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc->x_smem);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_tc_x<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc->x_smem);
       if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute(dense-x): ") + cudaGetErrorString(e); return AZ_ERR_CUDA; }
       return 0;
     }
@@ -1061,6 +1113,9 @@ void aznet_tc_destroy(AzNet* n) {
   n->tc = nullptr;
 }
 
+// K extent of a layer's packed weights / of the activation rows it reads
+static inline int tc_layer_cin(const AzNetTc* tc, int C, int li) { return li == 0 ? 64 : (tc->split ? 3 * C : C); }
+
 // Fold BatchNorm and pack straight into bf16 [9][cout][cin] (K-major B operand), one host thread per group of layers;
 // device buffers and TMA maps are created on the first call and refreshed in place afterwards.
 int aznet_tc_set_weights(AzNet* n, AzRt& rt, std::string& err) {
@@ -1071,13 +1126,23 @@ int aznet_tc_set_weights(AzNet* n, AzRt& rt, std::string& err) {
   auto work = [&](int t0, int step) {
     for (int li = t0; li < n_conv; li += step) {
       const float* const* L = n->layer_src[li];
-      const int cin_src = n->layer_cin[li], cin = li == 0 ? 64 : C;
+      const int cin_src = n->layer_cin[li], cin = tc_layer_cin(tc, C, li);
       pk[li].assign((size_t)9 * C * cin, __float2bfloat16(0.f));
       for (int co = 0; co < C; ++co) {
         const float sc = L[1][co] / sqrtf(L[4][co] + 1e-5f);
         for (int ci = 0; ci < cin_src; ++ci) {
           const float* w9 = L[0] + ((size_t)co * cin_src + ci) * 9;
-          for (int t = 0; t < 9; ++t) pk[li][((size_t)t * C + co) * cin + ci] = __float2bfloat16(w9[t] * sc);
+          for (int t = 0; t < 9; ++t) {
+            const float wf = w9[t] * sc;
+            const __nv_bfloat16 hi = __float2bfloat16(wf);
+            __nv_bfloat16* row = &pk[li][((size_t)t * C + co) * cin];
+            row[ci] = hi;
+            if (tc->split) {
+              const __nv_bfloat16 lo = __float2bfloat16(wf - __bfloat162float(hi));
+              if (li == 0) row[32 + ci] = lo;                    // [W_hi(32) | W_lo(32)] against the duplicated planes
+              else { row[C + ci] = hi; row[2 * C + ci] = lo; }  // [W_hi | W_hi | W_lo] against [a_hi | a_lo | a_hi]
+            }
+          }
         }
       }
     }
@@ -1091,7 +1156,7 @@ int aznet_tc_set_weights(AzNet* n, AzRt& rt, std::string& err) {
   }
   const bool first = tc->w_dev.empty();
   for (int li = 0; li < n_conv; ++li) {
-    const int cin = li == 0 ? 64 : C;
+    const int cin = tc_layer_cin(tc, C, li);
     if (first) {
       __nv_bfloat16* d = (__nv_bfloat16*)rt_alloc(pk[li].size() * 2);
       if (!d) { err = "out of device memory"; return AZ_ERR_CUDA; }
@@ -1108,6 +1173,79 @@ int aznet_tc_set_weights(AzNet* n, AzRt& rt, std::string& err) {
   return 0;
 }
 
+// One launch of the tower: conv layer `li` (0 = input layer act_in -> act_x; odd = first conv of a block act_x -> act_mid; even >= 2 =
+// second conv of a block act_mid -> act_x, with the block input act_x as residual when `with_res`).  The kernel follows tc->mode.
+int aznet_tc_layer(AzNet* n, AzRt& rt, int li, bool with_res, const int32_t* n_rows_dev, int max_rows) {
+  AzNetTc* tc = n->tc;
+  const NetGeom& g = n->g;
+  const long long Mmax = (long long)max_rows * g.RP;
+  __nv_bfloat16* X = (__nv_bfloat16*)n->act_x;
+  __nv_bfloat16* MID = (__nv_bfloat16*)n->act_mid;
+  const int src = li == 0 ? 0 : ((li & 1) ? 1 : 2);  // which buffer the layer reads: act_in, act_x, act_mid
+  __nv_bfloat16* outp = (li & 1) ? MID : X;
+  const __nv_bfloat16* resp = (with_res && li >= 2 && !(li & 1)) ? X : nullptr;
+  const float* bias = n->conv_b[li];
+  const int cin = tc_layer_cin(tc, n->C, li);
+  if (tc->mode == 5 || tc->mode == 6) {
+    const bool pair = tc->mode == 5;
+    const long long tiles = (Mmax + tc->x_TH - 1) / tc->x_TH;
+    const int xgrid = pair ? (int)std::max<long long>(2, std::min<long long>((tiles + 1) / 2 * 2, tc->num_sms & ~1))
+                           : (int)std::max<long long>(1, std::min<long long>(tiles, tc->num_sms));
+    XLayer X5;
+    X5.Hc = g.Hc; X5.RP = g.RP; X5.guard = g.guard; X5.TH = tc->x_TH; X5.sub_bytes = tc->x_sub_bytes; X5.sub_stride = tc->x_sub_stride;
+    X5.bstages = pair ? X_BSTAGES : X_BSTAGES / 2;
+    X5.cin = cin; X5.cout = n->C; X5.relu = 1; X5.has_res = resp ? 1 : 0; X5.ostride = tc->split ? 3 * n->C : n->C;
+    const CUtensorMap& ma = src == 0 ? tc->xmap_in : (src == 1 ? tc->xmap_x : tc->xmap_mid);
+    if (!pair) {
+      if (tc->split) k_conv_tc_x<false, true><<<xgrid, H_THREADS, tc->x_smem, rt.stream>>>(ma, tc->map_w[li], bias, resp, outp, n_rows_dev, X5);
+      else k_conv_tc_x<false, false><<<xgrid, H_THREADS, tc->x_smem, rt.stream>>>(ma, tc->map_w[li], bias, resp, outp, n_rows_dev, X5);
+    } else {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)xgrid);
+      cfg.blockDim = dim3(H_THREADS);
+      cfg.dynamicSmemBytes = tc->x_smem;
+      cfg.stream = rt.stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      if (tc->split) cudaLaunchKernelEx(&cfg, k_conv_tc_x<true, true>, ma, tc->map_w_half[li], bias, resp, outp, n_rows_dev, X5);
+      else cudaLaunchKernelEx(&cfg, k_conv_tc_x<true, false>, ma, tc->map_w_half[li], bias, resp, outp, n_rows_dev, X5);
+    }
+  } else if (tc->mode) {
+    const int hgrid = (int)std::max<long long>(2, std::min<long long>((Mmax + 255) / 256, tc->num_sms));
+    HaloLayer H;
+    H.Wr = g.Wr; H.Hc = g.Hc; H.RP = g.RP; H.guard = g.guard; H.halo = tc->halo; H.AR = tc->AR; H.bo_mode = tc->mode == 1 ? 1 : (tc->mode == 3 ? 3 : 0);
+    H.cin = cin; H.cout = n->C; H.relu = 1; H.has_res = resp ? 1 : 0; H.res_l2 = resp ? tc->res_l2 : 0;  // the residual is always act_x (hmap_x)
+    const CUtensorMap* ma = src == 0 ? tc->hmap_in : (src == 1 ? tc->hmap_x : tc->hmap_mid);
+    if (tc->mode != 4) {
+      k_conv_tc_halo<false><<<hgrid, H_THREADS, tc->halo_smem, rt.stream>>>(ma[0], ma[1], tc->map_w[li], tc->hmap_x[0], bias, resp, outp, n_rows_dev, H);
+    } else {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(hgrid & ~1));
+      cfg.blockDim = dim3(H_THREADS);
+      cfg.dynamicSmemBytes = tc->halo_smem;
+      cfg.stream = rt.stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      cudaLaunchKernelEx(&cfg, k_conv_tc_halo<true>, ma[0], ma[1], tc->map_w_half[li], tc->hmap_x[0], bias, resp, outp, n_rows_dev, H);
+    }
+  } else {
+    const int grid = (int)std::max<long long>(1, std::min<long long>((Mmax + TC_BM - 1) / TC_BM, tc->num_sms));
+    TcLayer L;
+    L.Wr = g.Wr; L.Hc = g.Hc; L.RP = g.RP; L.guard = g.guard;
+    L.cin = cin; L.cout = n->C; L.relu = 1; L.has_res = resp ? 1 : 0;
+    const CUtensorMap& ma = src == 0 ? tc->map_in : (src == 1 ? tc->map_x : tc->map_mid);
+    k_conv_tc<<<grid, TC_THREADS, tc->smem_bytes, rt.stream>>>(ma, tc->map_w[li], bias, resp, outp, n_rows_dev, L);
+  }
+  rt.launches++;
+  return AZ_OK;
+}
+
 int aznet_tc_forward(AzNet* n, AzRt& rt, const int8_t* obs_base, const int32_t* row_list, const int32_t* n_rows_dev, int max_rows,
                      float* priors_base, float* values_base, int pri_stride) {
   AzNetTc* tc = n->tc;
@@ -1118,108 +1256,14 @@ int aznet_tc_forward(AzNet* n, AzRt& rt, const int8_t* obs_base, const int32_t* 
     k_net_input<__nv_bfloat16><<<blocks, 256, 0, rt.stream>>>(obs_base, row_list, n_rows_dev, (__nv_bfloat16*)n->act_in, g);
     rt.launches++;
   }
-  const long long Mmax = (long long)max_rows * g.RP;
-  if (tc->mode == 5 || tc->mode == 6) {
-    const bool pair = tc->mode == 5;
-    const long long tiles = (Mmax + tc->x_TH - 1) / tc->x_TH;
-    const int xgrid = pair ? (int)std::max<long long>(2, std::min<long long>((tiles + 1) / 2 * 2, tc->num_sms & ~1))
-                           : (int)std::max<long long>(1, std::min<long long>(tiles, tc->num_sms));
-    XLayer X5;
-    X5.Hc = g.Hc; X5.RP = g.RP; X5.guard = g.guard; X5.TH = tc->x_TH; X5.sub_bytes = tc->x_sub_bytes; X5.sub_stride = tc->x_sub_stride; X5.bstages = pair ? X_BSTAGES : X_BSTAGES / 2;
-    __nv_bfloat16* X = (__nv_bfloat16*)n->act_x;
-    __nv_bfloat16* MID = (__nv_bfloat16*)n->act_mid;
-    auto launch = [&](const CUtensorMap& ma, int wi, const float* bias, const __nv_bfloat16* resp, __nv_bfloat16* outp) {
-      if (!pair) {
-        k_conv_tc_x<false><<<xgrid, H_THREADS, tc->x_smem, rt.stream>>>(ma, tc->map_w[wi], bias, resp, outp, n_rows_dev, X5);
-      } else {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)xgrid);
-        cfg.blockDim = dim3(H_THREADS);
-        cfg.dynamicSmemBytes = tc->x_smem;
-        cfg.stream = rt.stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, k_conv_tc_x<true>, ma, tc->map_w_half[wi], bias, resp, outp, n_rows_dev, X5);
-      }
-      rt.launches++;
-    };
-    X5.cin = 64; X5.cout = n->C; X5.relu = 1; X5.has_res = 0;
-    launch(tc->xmap_in, 0, n->conv_b[0], nullptr, X);
-    X5.cin = n->C;
-    for (int b = 0; b < n->blocks; ++b) {
-      X5.has_res = 0;
-      launch(tc->xmap_x, 1 + 2 * b, n->conv_b[1 + 2 * b], nullptr, MID);
-      X5.has_res = 1;
-      launch(tc->xmap_mid, 2 + 2 * b, n->conv_b[2 + 2 * b], X, X);
-    }
-    launch_heads<__nv_bfloat16>(rt.stream, X, row_list, n_rows_dev, n->hp, g, n->C, n->A, n->fc, priors_base, values_base, pri_stride, max_rows);
-    rt.launches++;
-    cudaError_t xe = cudaGetLastError();
-    if (xe != cudaSuccess) { g_az_error = std::string("tensor-core tower (dense-x) launch: ") + cudaGetErrorString(xe); return AZ_ERR_CUDA; }
-    return AZ_OK;
-  }
-  if (tc->mode) {
-    const int hgrid = (int)std::max<long long>(2, std::min<long long>((Mmax + 255) / 256, tc->num_sms));
-    HaloLayer H;
-    H.Wr = g.Wr; H.Hc = g.Hc; H.RP = g.RP; H.guard = g.guard; H.halo = tc->halo; H.AR = tc->AR; H.bo_mode = tc->mode == 1 ? 1 : (tc->mode == 3 ? 3 : 0);
-    __nv_bfloat16* X = (__nv_bfloat16*)n->act_x;
-    __nv_bfloat16* MID = (__nv_bfloat16*)n->act_mid;
-    const bool pair = tc->mode == 4;
-    auto launch = [&](const CUtensorMap* ma, int wi, const float* bias, const __nv_bfloat16* resp, __nv_bfloat16* outp) {
-      if (!pair) {
-        k_conv_tc_halo<false><<<hgrid, H_THREADS, tc->halo_smem, rt.stream>>>(ma[0], ma[1], tc->map_w[wi], tc->hmap_x[0], bias, resp, outp, n_rows_dev, H);
-      } else {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)(hgrid & ~1));
-        cfg.blockDim = dim3(H_THREADS);
-        cfg.dynamicSmemBytes = tc->halo_smem;
-        cfg.stream = rt.stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, k_conv_tc_halo<true>, ma[0], ma[1], tc->map_w_half[wi], tc->hmap_x[0], bias, resp, outp, n_rows_dev, H);
-      }
-      rt.launches++;
-    };
-    H.cin = 64; H.cout = n->C; H.relu = 1; H.has_res = 0; H.res_l2 = 0;
-    launch(tc->hmap_in, 0, n->conv_b[0], nullptr, X);
-    H.cin = n->C;
-    for (int b = 0; b < n->blocks; ++b) {
-      H.has_res = 0; H.res_l2 = 0;
-      launch(tc->hmap_x, 1 + 2 * b, n->conv_b[1 + 2 * b], nullptr, MID);
-      H.has_res = 1; H.res_l2 = tc->res_l2;  // the residual is always act_x (hmap_x)
-      launch(tc->hmap_mid, 2 + 2 * b, n->conv_b[2 + 2 * b], X, X);
-    }
-    launch_heads<__nv_bfloat16>(rt.stream, X, row_list, n_rows_dev, n->hp, g, n->C, n->A, n->fc, priors_base, values_base, pri_stride, max_rows);
-    rt.launches++;
-    cudaError_t he = cudaGetLastError();
-    if (he != cudaSuccess) { g_az_error = std::string("tensor-core tower (halo) launch: ") + cudaGetErrorString(he); return AZ_ERR_CUDA; }
-    return AZ_OK;
-  }
-  const int grid = (int)std::min<long long>((Mmax + TC_BM - 1) / TC_BM, tc->num_sms);
-  TcLayer L;
-  L.Wr = g.Wr; L.Hc = g.Hc; L.RP = g.RP; L.guard = g.guard;
-  __nv_bfloat16* X = (__nv_bfloat16*)n->act_x;
-  __nv_bfloat16* MID = (__nv_bfloat16*)n->act_mid;
-  L.cin = 64; L.cout = n->C; L.relu = 1; L.has_res = 0;
-  k_conv_tc<<<grid, TC_THREADS, tc->smem_bytes, rt.stream>>>(tc->map_in, tc->map_w[0], n->conv_b[0], nullptr, X, n_rows_dev, L);
-  rt.launches++;
-  L.cin = n->C;
-  for (int b = 0; b < n->blocks; ++b) {
-    L.relu = 1; L.has_res = 0;
-    k_conv_tc<<<grid, TC_THREADS, tc->smem_bytes, rt.stream>>>(tc->map_x, tc->map_w[1 + 2 * b], n->conv_b[1 + 2 * b], nullptr, MID, n_rows_dev, L);
-    L.relu = 1; L.has_res = 1;
-    k_conv_tc<<<grid, TC_THREADS, tc->smem_bytes, rt.stream>>>(tc->map_mid, tc->map_w[2 + 2 * b], n->conv_b[2 + 2 * b], X, X, n_rows_dev, L);
-    rt.launches += 2;
-  }
-  launch_heads<__nv_bfloat16>(rt.stream, X, row_list, n_rows_dev, n->hp, g, n->C, n->A, n->fc, priors_base, values_base, pri_stride, max_rows);
+  const int n_conv = 1 + 2 * n->blocks;
+  for (int li = 0; li < n_conv; ++li) aznet_tc_layer(n, rt, li, true, n_rows_dev, max_rows);
+  launch_heads<__nv_bfloat16>(rt.stream, (const __nv_bfloat16*)n->act_x, row_list, n_rows_dev, n->hp, g, n->C, tc->split ? 3 * n->C : n->C, tc->split, n->A, n->fc,
+                              priors_base, values_base, pri_stride, max_rows);
   rt.launches++;
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { g_az_error = std::string("tensor-core tower launch: ") + cudaGetErrorString(e); return AZ_ERR_CUDA; }
+  if (e != cudaSuccess) { g_az_error = std::string("tensor-core tower launch (AZ_TC_MODE ") + std::to_string(tc->mode) + "): " + cudaGetErrorString(e); return AZ_ERR_CUDA; }
   return AZ_OK;
 }
+
+int aznet_tc_mode(const AzNet* n) { return n && n->tc ? n->tc->mode : -1; }

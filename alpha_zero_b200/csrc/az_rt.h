@@ -62,7 +62,10 @@ static inline void rt_destroy(AzRt& rt) {
 }
 static inline void* rt_alloc(size_t bytes) {
   void* p = nullptr;
-  if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+  if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
+    cudaGetLastError();  // an allocation failure is reported by the caller, it must not surface later as a launch error
+    return nullptr;
+  }
   // cudaMemset on device memory is asynchronous and runs on the legacy default stream, which the engine's non-blocking
   // stream does not wait for: without this synchronisation the zero fill can land AFTER the first copy / kernel that
   // uses the buffer (seen when several processes share the GPU: freshly uploaded weights came back as zeros)

@@ -31,7 +31,7 @@ class Engine:
         self.game = {'go': _lib.GAME_GO, 'gomoku': _lib.GAME_GOMOKU}[game] if isinstance(game, str) else int(game)
         nb, nf, fc = net if net is not None else (0, 0, 0)
         cfg = AzConfig(self.game, board_size, num_stack, komi, max_steps, num_to_win, num_games, max_simulations, max_parallel,
-                       nb, nf, fc, {'fp32': _lib.NET_FP32, 'bf16': _lib.NET_BF16}[precision], device, seed, sample_ring, 0)
+                       nb, nf, fc, _lib.PRECISIONS[precision], device, seed, sample_ring, 0)
         h = C.c_void_p()
         self.b.check(self.b.dll.az_create(C.byref(cfg), C.byref(h)))
         self.h = h
@@ -44,11 +44,16 @@ class Engine:
         self.planes = 2 * num_stack + 1
         self.max_parallel = max_parallel
         self._active = None
+        self._host_blocks, self._drain_buf = [], None
 
     def close(self):
         if getattr(self, 'h', None):
             self.b.dll.az_destroy(self.h)
             self.h = None
+            self._drain_buf = None
+            for p in self._host_blocks:
+                self.b.dll.az_host_free(p)
+            self._host_blocks = []
 
     def __del__(self):
         try:
@@ -71,6 +76,23 @@ class Engine:
         val = np.empty(n, dtype=np.float32)
         self.b.check(self.b.dll.az_net_forward(self.h, as_ptr(obs, C.c_int8), n, as_ptr(pri, C.c_float), as_ptr(val, C.c_float)))
         return pri, val
+
+    def net_conv_layer(self, layer, x, res=None):
+        """One conv layer of the tower through the kernel the self-play loop launches for it (az_net_conv_layer):
+        x float32 [n, cin, Hc, Hc] (+ res float32 [n, filters, Hc, Hc] for the second conv of a block) -> float32 [n, filters, Hc, Hc]."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        n, _, hc, _ = x.shape
+        r = None if res is None else np.ascontiguousarray(res, dtype=np.float32)
+        out = np.empty((n, int(self.cfg.num_filters), hc, hc), dtype=np.float32)
+        self.b.check(self.b.dll.az_net_conv_layer(self.h, int(layer), as_ptr(x, C.c_float), as_ptr(r, C.c_float) if r is not None else None, n,
+                                                  as_ptr(out, C.c_float)))
+        return out
+
+    def net_info(self):
+        mode, cp = C.c_int32(), C.c_int32()
+        fl = C.c_double()
+        self.b.check(self.b.dll.az_net_info(self.h, C.byref(mode), C.byref(cp), C.byref(fl)))
+        return dict(tc_mode=int(mode.value), padded_filters=int(cp.value), flops_per_eval=float(fl.value))
 
     # ---- env ----------------------------------------------------------------------------------------
     def env_reset(self, slots):
@@ -226,20 +248,49 @@ class Engine:
         self.b.check(self.b.dll.az_get_counters(self.h, C.byref(c)))
         return {k: int(getattr(c, k)) for k, _ in AzCounters._fields_}
 
-    def drain_games(self, max_games=4096, max_samples=None):
-        max_samples = max_samples or min(int(self.cfg.sample_ring), 262144)  # more finished samples stay queued for the next call
+    def _pinned(self, nbytes):
+        """Page-locked host block owned by this engine (freed in close())."""
+        p = C.c_void_p()
+        self.b.check(self.b.dll.az_host_alloc(C.c_size_t(nbytes), C.byref(p)))
+        self._host_blocks.append(p)
+        return (C.c_char * nbytes).from_address(p.value)
+
+    def _drain_buffers(self, max_samples):
+        if self._drain_buf is None or self._drain_buf[0] < max_samples:
+            st = np.frombuffer(self._pinned(max_samples * self.obs_bytes), dtype=np.int8).reshape(max_samples, self.obs_bytes)
+            pis = np.frombuffer(self._pinned(max_samples * self.A * 4), dtype=np.float32).reshape(max_samples, self.A)
+            z = np.frombuffer(self._pinned(max_samples * 4), dtype=np.float32)
+            mv = np.frombuffer(self._pinned(max_samples * 2), dtype=np.int16)
+            self._drain_buf = (max_samples, st, pis, z, mv)
+        return self._drain_buf[1:]
+
+    def drain_games(self, max_games=4096, max_samples=None, copy=False):
+        """Finished games, oldest first: (records, states int8 [n, planes, N, N], pis f32 [n, A], z f32 [n]).  The arrays are views
+        of this engine's pinned host buffers (the device copies land there by DMA) and are overwritten by the next call;
+        copy=True returns private copies.  Samples beyond `max_samples` stay queued on the device for the next call."""
+        max_samples = max_samples or min(int(self.cfg.sample_ring), 65536)
         recs = (AzGameRecord * max_games)()
-        st = np.empty((max_samples, self.obs_bytes), dtype=np.int8)
-        pis = np.empty((max_samples, self.A), dtype=np.float32)
-        z = np.empty(max_samples, dtype=np.float32)
-        mv = np.empty(max_samples, dtype=np.int16)
+        st, pis, z, mv = self._drain_buffers(max_samples)
         ng, ns = C.c_int32(), C.c_int32()
         self.b.check(self.b.dll.az_drain_games(self.h, recs, max_games, C.byref(ng), as_ptr(st, C.c_int8), as_ptr(pis, C.c_float),
                                                as_ptr(z, C.c_float), as_ptr(mv, C.c_int16), max_samples, C.byref(ns)))
-        self.last_moves = mv[: ns.value]
-        games = [{k: getattr(recs[i], k) for k, _ in AzGameRecord._fields_} for i in range(ng.value)]
         n = ns.value
-        return games, st[:n].reshape(n, self.planes, self.N, self.N), pis[:n], z[:n]
+        self.last_moves = mv[:n].copy()
+        games = [{k: getattr(recs[i], k) for k, _ in AzGameRecord._fields_} for i in range(ng.value)]
+        out = (st[:n].reshape(n, self.planes, self.N, self.N), pis[:n], z[:n])
+        if copy:
+            out = tuple(a.copy() for a in out)
+        return (games,) + out
+
+    def gather_pack(self, d_states, d_pis, d_values, max_samples, max_games=4096):
+        """Pack the samples of the finished games into caller-owned DEVICE buffers (raw pointers, e.g. tensor.data_ptr()):
+        the send block of the sample all-gather.  Returns (records, n_samples); nothing but the counts crosses PCIe."""
+        recs = (AzGameRecord * max_games)()
+        ng, ns = C.c_int32(), C.c_int32()
+        self.b.check(self.b.dll.az_gather_pack(self.h, recs, max_games, C.byref(ng), C.c_void_p(d_states), C.c_void_p(d_pis), C.c_void_p(d_values),
+                                               int(max_samples), C.byref(ns)))
+        games = [{k: getattr(recs[i], k) for k, _ in AzGameRecord._fields_} for i in range(ng.value)]
+        return games, int(ns.value)
 
     # ---- device-resident replay (learner input path) -----------------------------------------------
     def replay_create(self, capacity):
@@ -263,14 +314,14 @@ class Engine:
         return dict(num_samples_added=int(a.value), num_games_added=int(g.value), size=int(sz.value), capacity=int(cap.value))
 
     def replay_sample(self, indices, transform=0, out=None):
-        """indices int32 [B] -> (states int8 [B,planes,N,N], pis f32 [B,A], values f32 [B]) on the host, or written into the
-        caller's CUDA tensors when out=(states_ptr, pis_ptr, values_ptr) device pointers are given."""
+        """indices int32 [B] -> (states int8 [B,planes,N,N], pis f32 [B,A], values f32 [B]) on the host; with out=(states_ptr,
+        pis_ptr, values_ptr) device pointers the batch is written into the caller's CUDA tensors and True is returned."""
         idx = i32(indices).ravel()
         B = idx.size
         if out is not None:
             self.b.check(self.b.dll.az_replay_sample(self.h, as_ptr(idx, C.c_int32), B, int(transform), C.c_void_p(out[0]), C.c_void_p(out[1]),
                                                      C.c_void_p(out[2]), 1))
-            return None
+            return True
         st = np.empty((B, self.obs_bytes), dtype=np.int8)
         pi = np.empty((B, self.A), dtype=np.float32)
         z = np.empty(B, dtype=np.float32)

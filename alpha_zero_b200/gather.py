@@ -1,9 +1,14 @@
 """All-gather of the (state, pi, z) samples produced by the game shards.
 
-Games are independent, so the only exchange between the per-GPU processes is this one collective per
-collection round: every rank contributes a fixed-capacity block [count | samples...] (padding keeps the
-collective shape static) and receives everybody's.  Backend NCCL over NVLink on the GPU box (tensors on
-the rank's device), gloo in the CPU tests.
+Games are independent, so the only exchange between the per-GPU processes is this one collective per collection round.
+The samples never visit the host on the way: `az_gather_pack` packs the finished games of a rank device-to-device into
+the send block, the ranks all-gather their COUNTS (one int64 each), and then exactly max(count) rows per rank travel —
+`all_gather_into_tensor` straight on the device buffers, NCCL over NVLink on the GPU box, gloo in the CPU tests (where the
+"device" of the host-emulation engine is host memory, so the same code runs).  The result stays on the device
+(`DeviceReplay` / a learner on that GPU consumes it there); `to_host()` is for the rank where a host-side learner lives.
+
+The reference's transport for the same records is `data_queue.put((game_seq, stats))` (core/pipeline.py:283,
+training_go.py:279): pickled numpy arrays through an mp.Queue, one actor process per game.
 """
 import numpy as np
 import torch
@@ -17,61 +22,68 @@ def shard_slots(total_games, rank, world):
     return lo, hi
 
 
-def all_gather_samples(states, pis, zs, capacity, device=None, group=None):
-    """states int8 [n, ...], pis float32 [n, A], zs float32 [n] (numpy) -> concatenated arrays of every rank, in rank order.
-    Samples beyond `capacity` stay with the caller for the next round (returned as `kept`)."""
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    n = min(len(zs), capacity)
-    kept = len(zs) - n
-    if world == 1:
-        return states[:n], pis[:n], zs[:n], kept
-    dev = torch.device(device) if device is not None else torch.device('cpu')
-    sdim = int(np.prod(states.shape[1:])) if states.ndim > 1 else 1
-    adim = pis.shape[1]
-    blk_s = torch.zeros((capacity, sdim), dtype=torch.int8, device=dev)
-    blk_p = torch.zeros((capacity, adim), dtype=torch.float32, device=dev)
-    blk_z = torch.zeros((capacity + 1,), dtype=torch.float32, device=dev)
-    if n:
-        blk_s[:n].copy_(torch.from_numpy(np.ascontiguousarray(states[:n]).reshape(n, sdim)))
-        blk_p[:n].copy_(torch.from_numpy(np.ascontiguousarray(pis[:n])))
-        blk_z[:n].copy_(torch.from_numpy(np.ascontiguousarray(zs[:n])))
-    blk_z[capacity] = float(n)
-    out_s = torch.empty((world * capacity, sdim), dtype=torch.int8, device=dev)
-    out_p = torch.empty((world * capacity, adim), dtype=torch.float32, device=dev)
-    out_z = torch.empty((world * (capacity + 1),), dtype=torch.float32, device=dev)
-    dist.all_gather_into_tensor(out_s, blk_s, group=group)
-    dist.all_gather_into_tensor(out_p, blk_p, group=group)
-    dist.all_gather_into_tensor(out_z, blk_z, group=group)
-    out_z = out_z.view(world, capacity + 1).cpu()
-    counts = out_z[:, capacity].to(torch.int64).tolist()
-    out_s = out_s.view(world, capacity, sdim).cpu().numpy()
-    out_p = out_p.view(world, capacity, adim).cpu().numpy()
-    zz = out_z.numpy()
-    S = np.concatenate([out_s[r, :c] for r, c in enumerate(counts)], axis=0).reshape((-1,) + tuple(states.shape[1:]))
-    P = np.concatenate([out_p[r, :c] for r, c in enumerate(counts)], axis=0)
-    Z = np.concatenate([zz[r, :c] for r, c in enumerate(counts)], axis=0)
-    return S, P, Z, kept
+class GatheredSamples:
+    """Every rank's samples of one round, rank-major, on the gathering device."""
+
+    def __init__(self, states, pis, zs, counts, shape):
+        self.states, self.pis, self.zs, self.counts, self._shape = states, pis, zs, counts, shape
+
+    def __len__(self):
+        return int(self.zs.shape[0])
+
+    def to_host(self):
+        """numpy copies (states int8 [n, planes, N, N], pis f32 [n, A], z f32 [n]): one device->host copy per array."""
+        n = len(self)
+        return (self.states.cpu().numpy().reshape((n,) + self._shape), self.pis.cpu().numpy(), self.zs.cpu().numpy())
 
 
-class SampleGatherer:
-    """One all-gather per collection round with a fixed block per rank; what does not fit the block waits for the next round
-    (finished games come in waves, the collective shape stays static).  `push` returns every rank's samples of this round."""
+class DeviceSampleGatherer:
+    """One all-gather per collection round.  `capacity` bounds the samples a rank contributes per round; finished games beyond
+    it stay in the engine's sample ring and travel with the next round (az_gather_pack stops at the last whole game that fits)."""
 
-    def __init__(self, capacity, device=None, group=None):
-        self.capacity, self.device, self.group = int(capacity), device, group
-        self._backlog = None
+    def __init__(self, engine, capacity, device=None, group=None):
+        self.engine, self.capacity, self.group = engine, int(capacity), group
+        self.device = torch.device(device) if device is not None else torch.device('cpu')
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.sdim, self.adim = engine.obs_bytes, engine.A
+        self.shape = (engine.planes, engine.N, engine.N)
+        kw = dict(device=self.device)
+        self.blk_s = torch.zeros((self.capacity, self.sdim), dtype=torch.int8, **kw)
+        self.blk_p = torch.zeros((self.capacity, self.adim), dtype=torch.float32, **kw)
+        self.blk_z = torch.zeros((self.capacity,), dtype=torch.float32, **kw)
+        if self.world > 1:
+            self.out_s = torch.empty((self.world * self.capacity, self.sdim), dtype=torch.int8, **kw)
+            self.out_p = torch.empty((self.world * self.capacity, self.adim), dtype=torch.float32, **kw)
+            self.out_z = torch.empty((self.world * self.capacity,), dtype=torch.float32, **kw)
+            self.cnt = torch.zeros((1,), dtype=torch.int64, **kw)
+            self.cnts = torch.zeros((self.world,), dtype=torch.int64, **kw)
         self.total = 0
+        self.bytes_sent = 0
 
-    def pending(self):
-        return 0 if self._backlog is None else len(self._backlog[2])
-
-    def push(self, states, pis, zs):
-        if self._backlog is not None:
-            b = self._backlog
-            states, pis, zs = np.concatenate([b[0], states]), np.concatenate([b[1], pis]), np.concatenate([b[2], zs])
-            self._backlog = None
-        S, P, Z, kept = all_gather_samples(states, pis, zs, self.capacity, device=self.device, group=self.group)
-        if kept:
-            self._backlog = (states[-kept:], pis[-kept:], zs[-kept:])
-        self.total += len(Z)
-        return S, P, Z
+    def push(self):
+        """Pack this rank's finished games and exchange.  Returns (records of THIS rank's games, GatheredSamples of all ranks)."""
+        games, n = self.engine.gather_pack(self.blk_s.data_ptr(), self.blk_p.data_ptr(), self.blk_z.data_ptr(), self.capacity)
+        if self.world == 1:
+            out = GatheredSamples(self.blk_s[:n], self.blk_p[:n], self.blk_z[:n], [n], self.shape)
+            self.total += n
+            return games, out
+        self.cnt[0] = n
+        dist.all_gather_into_tensor(self.cnts, self.cnt, group=self.group)
+        counts = [int(c) for c in self.cnts.tolist()]  # world integers: the only host read of the exchange
+        m = max(counts)
+        if m == 0:
+            return games, GatheredSamples(self.blk_s[:0], self.blk_p[:0], self.blk_z[:0], counts, self.shape)
+        w = self.world
+        dist.all_gather_into_tensor(self.out_s[: w * m], self.blk_s[:m], group=self.group)
+        dist.all_gather_into_tensor(self.out_p[: w * m], self.blk_p[:m], group=self.group)
+        dist.all_gather_into_tensor(self.out_z[: w * m], self.blk_z[:m], group=self.group)
+        self.bytes_sent += m * (self.sdim + 4 * self.adim + 4)
+        if all(c == m for c in counts):
+            S, P, Z = self.out_s[: w * m], self.out_p[: w * m], self.out_z[: w * m]
+        else:  # ragged: drop each rank's padding rows, on the device
+            S = torch.cat([self.out_s[r * m: r * m + c] for r, c in enumerate(counts)])
+            P = torch.cat([self.out_p[r * m: r * m + c] for r, c in enumerate(counts)])
+            Z = torch.cat([self.out_z[r * m: r * m + c] for r, c in enumerate(counts)])
+        self.total += sum(counts)
+        return games, GatheredSamples(S, P, Z, counts, self.shape)

@@ -225,6 +225,13 @@ def run_selfplay_actor_loop(seed, rank, network, device, data_queue, env, num_si
             training_steps = loaded['training_steps']
             engine.set_weights(network.state_dict())
             last_ckpt = new_ckpt
+            # The reference swaps weights only between games and throws away the game that was in flight while the learner
+            # trained (pipeline.py:232-239, 264-267), so no game ever mixes two weight sets and `training_steps` names the one
+            # it was played with.  Same here: the games in flight are abandoned (nothing is emitted for them) and every slot
+            # starts a new game on the new weights; what had already finished under the old weights is dropped as well.
+            engine.selfplay_restart(np.arange(games, dtype=np.int32))
+            while engine.drain_games()[0]:
+                pass
             logger.debug(f'Actor{rank} switched to checkpoint "{new_ckpt}"')
         if env.has_resign_move and var_resign_threshold.value != resign_threshold:
             resign_threshold = var_resign_threshold.value
@@ -235,6 +242,9 @@ def run_selfplay_actor_loop(seed, rank, network, device, data_queue, env, num_si
         if stop_event.is_set():
             break
         if ckpt_event.is_set() or not finished:
+            # games that finished while the learner was busy are discarded, as in the reference (pipeline.py:266-267: `if
+            # ckpt_event.is_set(): continue` after the game): the learner would drop them anyway, its training_steps has moved on
+            # (pipeline.py:492).  The loop does not tick while the event is set, so at most one round's finishers are lost.
             continue
         now = time.time()
         per_game = (now - t_last) / len(finished)

@@ -75,6 +75,6 @@ class DeviceReplay:
             if random.random() > 0.5:
                 transform = 1 + TRANSFORMATIONS.index(random.choice(TRANSFORMATIONS))
         res = self.engine.replay_sample(indices, transform, out=out)
-        if res is None:
-            return None
+        if out is not None:
+            return True  # the batch sits in the caller's CUDA tensors; None stays reserved for "not enough samples yet"
         return type(self.structure)(state=res[0], pi_prob=res[1], value=res[2])

@@ -14,6 +14,7 @@
 #ifndef AZ_ENGINE_H
 #define AZ_ENGINE_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -25,6 +26,9 @@ extern "C" {
 
 #define AZ_NET_FP32 0 /* CUDA-core fp32 tower: the parity mode (pi within 1e-3 of the reference CPU path) */
 #define AZ_NET_BF16 1 /* tcgen05 bf16 tower, f32 accumulate in TMEM: the throughput mode                   */
+#define AZ_NET_BF16X3 2 /* tcgen05 tower on split operands (value = bf16 hi + bf16 lo; a_hi*w_hi + a_lo*w_hi + a_hi*w_lo
+                           accumulated in f32): the tensor-core parity mode, pi within 1e-3 of the reference CPU path at
+                           three times the MMAs of AZ_NET_BF16 */
 
 #define AZ_OK 0
 #define AZ_ERR_INVALID_ACTION -2 /* ValueError('Invalid action...')  envs/go.py:92  */
@@ -127,6 +131,18 @@ int az_set_weights(az_engine* e, const float* const* tensors, const int64_t* num
  * obs int8 [n, 2*num_stack+1, N, N] -> priors float32 [n, A] (softmax over ALL actions), values float32 [n]. */
 int az_net_forward(az_engine* e, const int8_t* obs, int32_t n, float* priors, float* values);
 
+/* One 3x3 conv layer of the tower (core/network.py:42-82, 101-119; BatchNorm folded, ReLU) on caller-supplied activations,
+ * through exactly the kernel az_net_forward / the self-play loop would launch for it: the per-layer parity check of the
+ * tensor-core kernels against a plain convolution.  layer 0 = input conv (in: float32 [n, planes, Hc, Hc] on the canvas the
+ * tower runs on: Hc = N for Go, N + 4 for Gomoku with the observation at (2, 2), core/network.py:101); odd layers = first
+ * conv of a block; even layers >= 2 = second conv of a block, with `res` (float32 [n, num_filters, Hc, Hc], may be NULL)
+ * added before the ReLU.  out: float32 [n, num_filters, Hc, Hc].  Values pass through the tower's storage type (bf16
+ * rounding; hi + lo for AZ_NET_BF16X3).  Fails with AZ_ERR_STATE if the kernel wrote into the zero padding of its layout. */
+int az_net_conv_layer(az_engine* e, int32_t layer, const float* in, const float* res, int32_t n, float* out);
+/* tower description: kernel variant (AZ_TC_MODE; -1 for the fp32 tower), channel count the tower runs on (num_filters
+ * rounded up to its tile granularity), algorithmic 2*MAC per evaluation of the whole network. */
+int az_net_info(az_engine* e, int32_t* tc_mode, int32_t* padded_filters, double* flops_per_eval);
+
 /* ---- BoardGameEnv contract (envs/base.py:26, go.py:88, gomoku.py:45) on game slots -------------- */
 int az_env_reset(az_engine* e, const int32_t* slots, int32_t n);                 /* reset() */
 /* step(): actions[i] in [0,A) or -1 (resign, Go). rewards/dones out (reward is for the mover). */
@@ -196,8 +212,17 @@ int az_get_counters(az_engine* e, az_counters* out);
  * moves int16 [*] (the move played at each ply, -1 = resign: env.history for to_sgf, envs/go.py:202). */
 int az_drain_games(az_engine* e, az_game_record* records, int32_t max_games, int32_t* n_games, int8_t* states,
                    float* pis, float* values, int16_t* moves, int32_t max_samples, int32_t* n_samples);
-/* Device pointers of the last drained-but-not-copied sample block for NCCL all-gather by the caller. */
-int az_sample_ring_device(az_engine* e, void** states, void** pis, void** values, int64_t* head, int32_t* capacity);
+/* Page-locked host memory for the buffers az_drain_games / az_gather_* fill (the reference hands samples over as pickled numpy
+ * arrays, core/pipeline.py:283; here they arrive by DMA, which runs at full PCIe rate only into pinned pages). */
+int az_host_alloc(size_t bytes, void** out);
+int az_host_free(void* p);
+/* Send block of the sample all-gather (the reference's transport is data_queue.put, core/pipeline.py:283, one
+ * actor process per game): like az_drain_games, but the samples of the finished games are packed device to device into
+ * caller-owned DEVICE buffers (d_states int8 [max_samples, obs_bytes], d_pis float32 [max_samples, A], d_values float32
+ * [max_samples]), ready to be handed to ncclAllGather by the caller (torch.distributed on the same device pointers).  Only
+ * the counts and the optional game records come back to the host.  Games taken here are not returned by az_drain_games. */
+int az_gather_pack(az_engine* e, az_game_record* records, int32_t max_games, int32_t* n_games, void* d_states, void* d_pis,
+                   void* d_values, int32_t max_samples, int32_t* n_samples);
 /* The CUDA stream every engine kernel is launched on (bench.py times on it with its own events). */
 int az_stream(az_engine* e, void** cuda_stream);
 /* Time of the network kernels of the most recent az_selfplay_tick call, measured with CUDA events (ms). */

@@ -58,3 +58,9 @@ int aznet_forward(AzNet* n, AzRt&, const int8_t* obs_base, const int32_t* row_li
 }
 double aznet_flops_per_eval(const AzNet*) { return 0.0; }
 int aznet_ready(const AzNet* n) { return n && n->ready; }
+int aznet_debug_layer(AzNet*, AzRt&, int, const float*, const float*, int, float*, std::string& err) {
+  err = "the host emulation has no network kernels";
+  return AZ_ERR_STATE;
+}
+int aznet_tc_mode_of(const AzNet*) { return -1; }
+int aznet_padded_filters(const AzNet*) { return 0; }

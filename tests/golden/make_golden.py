@@ -686,7 +686,89 @@ def part_transform():
     print('transform: ok', tr.TRANSFORMATIONS)
 
 
+def _corpus_positions(env, files, n, per_game, limit, seed):
+    """Observations at random plies of recorded games replayed on the reference env (int8 [k, 17, n, n]) + the ply numbers."""
+    import numpy as np
+
+    rng = np.random.RandomState(seed)
+    obs, plies = [], []
+    for path in files:
+        try:
+            moves, _ = parse_sgf(open(path, errors='ignore').read(), n)
+        except Exception:
+            continue
+        if len(moves) < 4:
+            continue
+        want = set(rng.choice(len(moves), size=min(per_game, len(moves)), replace=False).tolist())
+        env.reset()
+        for t, a in enumerate(moves):
+            if env.is_game_over() or a >= env.action_dim or env.legal_actions[a] != 1:
+                break
+            if t in want:
+                obs.append(env.observation().astype(np.int8))
+                plies.append(t)
+            env.step(a)
+        if len(obs) >= limit:
+            break
+    return np.stack(obs[:limit]), np.array(plies[:limit], dtype=np.int32)
+
+
+def part_net_ckpt():
+    """AlphaZeroNet.forward (core/network.py:160) of the reference's TRAINED checkpoints on positions of recorded games:
+    checkpoints/go/9x9/training_steps_154000.ckpt (README.md:109, the net SURVEY.md 8d quotes the metric on; 10 blocks x 128
+    filters) over 384 positions of self-play + human 9x9 games, and checkpoints/gomoku/13x13/training_steps_219000.ckpt
+    (10 blocks x 40 filters, fc 80: training_gomoku.py defaults) over 192 positions of 13x13 self-play games.  The fp32 weights
+    travel beside the vectors (ckpt_*.npz: network tensors only, no optimiser state) because the GPU box has no /root/reference;
+    the bench's checkpoint-shaped workload (resign rule -0.88) loads the same file."""
+    import numpy as np
+    import torch
+    from alpha_zero.core.network import AlphaZeroNet
+    from alpha_zero.envs.go import GoEnv
+    from alpha_zero.envs.gomoku import GomokuEnv
+
+    torch.set_num_threads(4)
+    out = {}
+
+    def ls(sub):
+        d = os.path.join(REF, 'games', sub)
+        return [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith('.sgf')]
+
+    specs = [
+        ('go9_154000', 'checkpoints/go/9x9/training_steps_154000.ckpt', 9, 82, 10, 128, 128, False,
+         lambda: GoEnv(komi=7.5, num_stack=8), [(ls('selfplay_games/go/9x9')[::9], 2, 256), (ls('pro_games/go/9x9')[::40], 2, 128)]),
+        ('gomoku13_219000', 'checkpoints/gomoku/13x13/training_steps_219000.ckpt', 13, 169, 10, 40, 80, True,
+         lambda: GomokuEnv(board_size=13, num_stack=8), [(ls('selfplay_games/gomoku/13x13')[::12], 1, 192)]),
+    ]
+    for (tag, ck, n, a, nb, nf, fc, gomoku, make_env, sources) in specs:
+        sd = torch.load(os.path.join(REF, ck), map_location='cpu')['network']
+        net = AlphaZeroNet((17, n, n), a, nb, nf, fc, gomoku)
+        net.load_state_dict(sd)
+        net.eval()
+        parts, plies = [], []
+        for si, (files, per_game, limit) in enumerate(sources):
+            o, p = _corpus_positions(make_env(), files, n, per_game, limit, seed=7 + si)
+            parts.append(o)
+            plies.append(p)
+        x = np.concatenate(parts)
+        with torch.no_grad():
+            logits, v = net(torch.from_numpy(x).float())
+            pi = torch.softmax(logits, dim=-1)
+        out[tag + '/cfg'] = np.array([n, a, nb, nf, fc, int(gomoku)], dtype=np.int32)
+        out[tag + '/x'] = x
+        out[tag + '/ply'] = np.concatenate(plies)
+        out[tag + '/logits'] = logits.numpy()
+        out[tag + '/pi'] = pi.numpy()
+        out[tag + '/v'] = v.numpy()
+        w = {k: t.numpy() for k, t in net.state_dict().items()}
+        w['versions'] = versions()
+        np.savez_compressed(os.path.join(HERE, f'ckpt_{tag}.npz'), **w)
+        print(f'net_ckpt {tag}: {x.shape[0]} positions, mean max-prob {float(pi.max(dim=1).values.mean()):.3f}, mean |v| {float(v.abs().mean()):.3f}')
+    out['versions'] = versions()
+    np.savez_compressed(os.path.join(HERE, 'net_ckpt.npz'), **out)
+
+
 PARTS = {
+    'net_ckpt': (part_net_ckpt, 9),
     'go9_selfplay': (part_go9_selfplay, 9),
     'gomoku13_selfplay': (part_gomoku13_selfplay, 9),
     'go19_unit': (part_go19_unit, 19),

@@ -106,14 +106,18 @@ def test_dense_x_tower_equals_halo_tower_statistically(cuda, tag):
     assert np.abs(x['pi'] - h['pi']).mean() < 2.0 * h['mean_dpi'] + 1e-4  # the two kernels are as close to each other as to the emulation
 
 
-@pytest.mark.parametrize('mode', ['4'])
+@pytest.mark.parametrize('mode', ['4', '5'])
 @pytest.mark.parametrize('tag', ['go9_c2', 'gomoku13_c4'])
 def test_net_bf16_matches_bf16_emulation(cuda, tag, mode):
     """tcgen05 tower (bf16 operands, f32 accumulation in TMEM) vs a torch restatement that rounds weights and stored
     activations to bf16 at the same places (oracle/net.py:forward_bf16_emulated) on the golden positions (3 + 2 of them): pi
-    within 1e-2, v within 2e-2 for the halo kernel (AZ_TC_MODE=4).  With so few positions this is a spot check of one summation
-    order; the default dense-x kernel is compared on a population in test_dense_x_tower_equals_halo_tower_statistically.  The
-    distance to the fp32 reference must not exceed 2.5x the emulation's own: that distance is rounding, not a bug."""
+    within 1e-2, v within 2e-2 for the halo kernel (AZ_TC_MODE=4), 5e-2 for the default dense-x kernel (mode 5; measured 1.5e-2
+    on the Gomoku positions).  These random-init nets with randomised BatchNorm are chaotic — the emulation with float64
+    accumulation differs from itself by 2-5e-2 on single positions — so the tight statements about the default kernel are made
+    where rounding is not amplified: one layer at a time against a plain convolution
+    (test_gpu_net_layers.py::test_conv_layer_matches_plain_convolution, a few ulps) and the whole tower on the reference's
+    trained checkpoints against the reference's own forward (test_trained_checkpoint_forward_vs_reference).  The distance to
+    the fp32 reference must not exceed 2.5x the emulation's own: that distance is rounding, not a bug."""
     from alpha_zero_b200.engine import Engine
     from oracle import net as onet
 
@@ -164,19 +168,35 @@ def test_net_19x19_256_filters(cuda, precision):
     eng.close()
 
 
-@pytest.mark.parametrize('game', ['go9', 'gomoku13'])
-def test_search_with_cuda_net_vs_oracle(cuda, game):
-    """Fixed-seed positions: pi from the CUDA search + CUDA fp32 net vs the oracle search + torch fp32 net: within 1e-3;
-    legal masks bit-exact; z (game result) identical after playing the game out deterministically."""
+SEARCH_CASES = [
+    # (game, precision, weights): 'small' = the 2-block random-init golden net, 'ckpt' = the reference's trained checkpoint
+    ('go9', 'fp32', 'small'), ('gomoku13', 'fp32', 'small'),
+    ('go9', 'bf16x3', 'small'), ('go9', 'bf16x3', 'ckpt'), ('gomoku13', 'bf16x3', 'ckpt'),
+]
+
+
+@pytest.mark.parametrize('game,precision,weights', SEARCH_CASES, ids=['-'.join(c) for c in SEARCH_CASES])
+def test_search_with_cuda_net_vs_oracle(cuda, game, precision, weights):
+    """Fixed-seed positions: pi from the CUDA search + CUDA net (fp32 CUDA-core tower, and the split-bf16 tcgen05 tower) vs the
+    oracle search + torch fp32 net: within 1e-3; legal masks bit-exact; z (game result) identical after playing the game out
+    deterministically.  The search policy is a ratio of visit counts, so it is a discontinuous function of the network output:
+    the 1e-3 holds when no PUCT near-tie flips.  The fp32 tower (3e-6 from the reference forward) keeps every ply of the
+    random-init nets; the split-bf16 tower (1.5e-4) keeps every ply on the reference's trained checkpoints and on the random-init
+    Go net, while on the random-init Gomoku net with randomised BatchNorm (a chaotic net: bf16 moves its priors by up to 0.8) one
+    ply in 60 moved by two visits (0.021) when measured, which is why that combination is not part of the gate."""
     from alpha_zero_b200.engine import Engine
     from oracle import net as onet
     from oracle.boards import GoBoard, GomokuBoard
     from oracle.search import search
 
-    tag = f'{game}_small'
-    z, n, a, nb, nf, fc, gomoku, net = _net_case(tag)
-    sd = net.state_dict()
-    eng = Engine('gomoku' if gomoku else 'go', n, num_games=2, max_simulations=128, max_parallel=8, net=(nb, nf, fc), precision='fp32',
+    if weights == 'small':
+        z, n, a, nb, nf, fc, gomoku, net = _net_case(f'{game}_small')
+        sd = net.state_dict()
+    else:
+        from test_gpu_net_layers import _ckpt
+
+        z, sd, n, a, nb, nf, fc, gomoku = _ckpt('go9_154000' if game == 'go9' else 'gomoku13_219000')
+    eng = Engine('gomoku' if gomoku else 'go', n, num_games=2, max_simulations=128, max_parallel=8, net=(nb, nf, fc), precision=precision,
                  max_steps=60 if not gomoku else 0)
     eng.set_weights(sd)
     ev = onet.make_eval_func(sd, gomoku)
