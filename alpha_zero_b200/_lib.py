@@ -52,7 +52,7 @@ class AzGameRecord(C.Structure):
 # every symbol include/az_engine.h declares; tests/test_abi.py checks the shared library exports each one
 SYMBOLS = [
     'az_last_error', 'az_version', 'az_create', 'az_destroy', 'az_get_config', 'az_num_actions', 'az_obs_bytes',
-    'az_set_weights', 'az_net_forward', 'az_net_conv_layer', 'az_net_info', 'az_env_reset', 'az_env_step', 'az_env_observation', 'az_env_legal_actions',
+    'az_set_weights', 'az_set_weights_for', 'az_match_begin', 'az_match_tick', 'az_net_forward', 'az_net_conv_layer', 'az_net_info', 'az_env_reset', 'az_env_step', 'az_env_observation', 'az_env_legal_actions',
     'az_env_board', 'az_env_scalars', 'az_env_score', 'az_env_copy', 'az_env_state_bytes', 'az_env_export',
     'az_env_import', 'az_env_replay', 'az_search_begin', 'az_search_select', 'az_search_apply', 'az_search_result', 'az_search_commit',
     'az_search_run', 'az_selfplay_begin', 'az_selfplay_tick', 'az_selfplay_update', 'az_selfplay_restart', 'az_sync', 'az_get_counters', 'az_drain_games',

@@ -25,6 +25,7 @@ struct az_engine {
   std::vector<void*> allocs;
   size_t alloc_bytes = 0, alloc_failed = 0;  // dev_alloc bookkeeping: bytes held, size of the first failed request
   AzNet* net = nullptr;
+  AzNet* net2 = nullptr;  // second weight set (evaluation matches), created by az_set_weights_for(e, 1, ...)
   // staging
   int32_t *d_slots = nullptr, *d_aux = nullptr, *d_out = nullptr;
   float* d_fout = nullptr;
@@ -47,7 +48,11 @@ struct az_engine {
   // az_tick_profile: per-phase device time of the self-play tick, CUDA events on the engine stream
   // AZ_PIPELINE=1 (opt-in): two halves of the slots; the tree kernels of one half run on `tree_rt` while the network evaluates
   // the other half on `rt`
+  bool fused_tree = false;          // AZ_FUSED_TREE=1: serial tick with the fused apply -> advance -> collect pass (measured: no gain, off)
   bool pipeline = false;
+  int pipeline_mode = 0;            // 1: one launch per phase, 512-CTA grids; 2: persistent fused tree pass, <= one CTA per SM
+  unsigned int* d_work_ctr = nullptr;  // [2] game counters of the persistent tree pass, one per half
+  int num_sms = 148;
   AzRt tree_rt;
   bool prof_on = false;
   double prof_ms[5] = {0, 0, 0, 0, 0};  // collect+compact, network, apply, advance, whole tick
@@ -237,6 +242,8 @@ extern "C" int az_create(const az_config* cfg, az_engine** out) {
   E.priors = dev_alloc<float>(e, rows * d.Ap);
   E.values = dev_alloc<float>(e, rows);
   E.leaf_rows = dev_alloc<int32_t>(e, rows);
+  E.leaf_rows2 = dev_alloc<int32_t>(e, rows);
+  E.slot_net = dev_alloc<uint8_t>(e, G);
   E.leaf_total = dev_alloc<int32_t>(e, 8);  // [0..1] totals, [2] az_net_forward's count, [4..5] totals of the second half (pipeline)
   E.leaf_count = dev_alloc<int32_t>(e, G);
   E.leaf_pk = dev_alloc<int32_t>(e, rows * AZ_PATH);
@@ -282,9 +289,19 @@ extern "C" int az_create(const az_config* cfg, az_engine** out) {
   }
 #endif
   {
+    const char* ft = getenv("AZ_FUSED_TREE");
+    e->fused_tree = ft ? atoi(ft) != 0 : false;
+  }
+  {
     const char* pl = getenv("AZ_PIPELINE");
     e->pipeline = pl && atoi(pl) != 0 && d.node_cache && d.G >= 2 && e->net;
+    e->pipeline_mode = e->pipeline ? atoi(pl) : 0;
     if (e->pipeline) {
+      e->d_work_ctr = dev_alloc<unsigned int>(e, 2);
+      if (alloc_check(e, "az_create")) { az_destroy(e); return AZ_ERR_CUDA; }
+#ifndef AZ_EMU
+      cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->rt.device);
+#endif
 #ifndef AZ_EMU
       bool ok = cudaStreamCreateWithFlags(&e->tree_rt.stream, cudaStreamNonBlocking) == cudaSuccess;
       e->tree_rt.device = e->rt.device;
@@ -312,6 +329,7 @@ extern "C" int az_destroy(az_engine* e) {
   if (!e) return AZ_OK;
   rt_sync(e->rt);
   if (e->net) aznet_destroy(e->net);
+  if (e->net2) aznet_destroy(e->net2);
   for (void* p : e->allocs) rt_free(p);
 #ifndef AZ_EMU
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -361,6 +379,22 @@ extern "C" int az_set_weights(az_engine* e, const float* const* tensors, const i
   std::string err;
   int rc = aznet_set_weights(e->net, e->rt, tensors, numel, n_tensors, err);
   if (rc) return az_fail(rc, "az_set_weights: " + err);
+  return rt_sync(e->rt);
+}
+
+extern "C" int az_set_weights_for(az_engine* e, int32_t which, const float* const* tensors, const int64_t* numel, int32_t n_tensors) {
+  AZ_ENTER(e);
+  if (!e || !tensors || !numel) return az_fail(AZ_ERR_BAD_ARG, "null argument");
+  if (which == 0) return az_set_weights(e, tensors, numel, n_tensors);
+  if (which != 1) return az_fail(AZ_ERR_BAD_ARG, "az_set_weights_for: weight set must be 0 or 1");
+  if (!e->net) return az_fail(AZ_ERR_STATE, "engine was created without a network (num_filters == 0)");
+  std::string err;
+  if (!e->net2) {
+    e->net2 = aznet_create(e->E.d, e->cfg, e->rt, e->E.d.G * e->E.d.Pmax, err);
+    if (!e->net2) return az_fail(AZ_ERR_CUDA, "az_set_weights_for: second network: " + err);
+  }
+  int rc = aznet_set_weights(e->net2, e->rt, tensors, numel, n_tensors, err);
+  if (rc) return az_fail(rc, "az_set_weights_for: " + err);
   return rt_sync(e->rt);
 }
 
@@ -749,6 +783,7 @@ extern "C" int az_selfplay_begin(az_engine* e, const az_selfplay_params* p) {
   AzSearchCfg& s = e->E.s;
   s.selfplay = 1;
   s.host_noise = 0;
+  s.match = 0;
   s.warm_up_steps = p->warm_up_steps;
   s.check_resign_after = p->check_resign_after_steps;
   s.resign_threshold = p->resign_threshold;
@@ -804,16 +839,36 @@ static int selfplay_tick_pipelined(az_engine* e, int n_ticks) {
   const AzDims& d = e->E.d;
   const int g0[2] = {0, d.G / 2}, ng[2] = {d.G / 2, d.G - d.G / 2};
   int32_t* tot[2] = {e->E.leaf_total, e->E.leaf_total + 4};
-  auto collect = [&](int h) {
-    AZ_LAUNCH_WARPS(e->tree_rt, k_collect_r, ng[h], d, e->E, g0[h]);
+  const bool fused = e->pipeline_mode >= 2;
+  // tree pass of half h: the requested phases (AZ_PH_*), then - when leaves were collected - the compaction of its leaf rows
+  auto tree_pass = [&](int h, int phases) {
+    if (fused) {
+      rt_zero(e->tree_rt, e->d_work_ctr + h, sizeof(unsigned int));
 #ifdef AZ_EMU
-    k_compact_r(e->E, g0[h], ng[h], tot[h]);
+      k_tree_p(e->E, g0[h], ng[h], phases, e->d_work_ctr + h);
 #else
-    k_compact_r<<<1, 128, 0, e->tree_rt.stream>>>(e->E, g0[h], ng[h], tot[h]);
+      const int grid = std::min(e->num_sms, (ng[h] + AZ_WPB - 1) / AZ_WPB);
+      k_tree_p<<<grid, AZ_WPB * 32, AZ_WPB * az_sim_stride(d), e->tree_rt.stream>>>(e->E, g0[h], ng[h], phases, e->d_work_ctr + h);
+#endif
+      e->tree_rt.launches++;
+    } else {
+      if (phases & AZ_PH_APPLY) AZ_LAUNCH_WARPS(e->tree_rt, k_apply_r, ng[h], d, e->E, g0[h]);
+      if (phases & AZ_PH_ADVANCE) AZ_LAUNCH_WARPS(e->tree_rt, k_advance_r, ng[h], d, e->E, g0[h]);
+      if (phases & AZ_PH_COLLECT) AZ_LAUNCH_WARPS(e->tree_rt, k_collect_r, ng[h], d, e->E, g0[h]);
+    }
+    if (phases & AZ_PH_COLLECT) {
+#ifdef AZ_EMU
+      k_compact_r(e->E, g0[h], ng[h], tot[h]);
+#else
+      k_compact_r<<<1, 128, 0, e->tree_rt.stream>>>(e->E, g0[h], ng[h], tot[h]);
+#endif
+      e->tree_rt.launches++;
+    }
+#ifndef AZ_EMU
     cudaEventRecord(e->ev_tree[h], e->tree_rt.stream);
 #endif
-    e->tree_rt.launches++;
   };
+  auto collect = [&](int h) { tree_pass(h, AZ_PH_COLLECT); };
 #ifndef AZ_EMU
   // everything queued on the engine stream so far (weights, earlier calls) happens before the tree stream starts
   cudaEventRecord(e->ev_p0, e->rt.stream);
@@ -835,12 +890,7 @@ static int selfplay_tick_pipelined(az_engine* e, int n_ticks) {
       cudaEventRecord(e->ev_net[h], e->rt.stream);
       cudaStreamWaitEvent(e->tree_rt.stream, e->ev_net[h], 0);
 #endif
-      AZ_LAUNCH_WARPS(e->tree_rt, k_apply_r, ng[h], d, e->E, g0[h]);
-      AZ_LAUNCH_WARPS(e->tree_rt, k_advance_r, ng[h], d, e->E, g0[h]);
-      if (t < n_ticks - 1) collect(h);
-#ifndef AZ_EMU
-      else cudaEventRecord(e->ev_tree[h], e->tree_rt.stream);
-#endif
+      tree_pass(h, AZ_PH_APPLY | AZ_PH_ADVANCE | (t < n_ticks - 1 ? AZ_PH_COLLECT : 0));
     }
   }
 #ifndef AZ_EMU
@@ -876,6 +926,38 @@ extern "C" int az_selfplay_tick(az_engine* e, int32_t n_ticks) {
 #else
 #define AZ_PROF_MARK(k) do { } while (0)
 #endif
+  if (e->fused_tree && !e->prof_on && d.node_cache && n_ticks > 0) {
+    // Fused tree pass: expand/backup -> move / re-root -> leaf collection of a game run back to back in one warp (games are
+    // independent), one launch instead of three and one straggler tail instead of three.  The per-phase profile (az_tick_profile)
+    // keeps the separate launches below.
+    auto tree_pass = [&](int phases) {
+#ifdef AZ_EMU
+      k_tree_p(e->E, 0, d.G, phases, nullptr);
+      if (phases & AZ_PH_COLLECT) k_compact(e->E, d.G);
+#else
+      k_tree_p<<<(d.G + AZ_WPB - 1) / AZ_WPB, AZ_WPB * 32, AZ_WPB * az_sim_stride(d), e->rt.stream>>>(e->E, 0, d.G, phases, nullptr);
+      if (phases & AZ_PH_COLLECT) k_compact<<<1, 1024, 0, e->rt.stream>>>(e->E, d.G);
+#endif
+      e->rt.launches += (phases & AZ_PH_COLLECT) ? 2 : 1;
+    };
+    tree_pass(AZ_PH_COLLECT);
+    for (int t = 0; t < n_ticks; ++t) {
+#ifndef AZ_EMU
+      if (t == n_ticks - 1) cudaEventRecord(e->ev0, e->rt.stream);
+#endif
+      int rc = aznet_forward(e->net, e->rt, e->E.leaf_obs, e->E.leaf_rows, e->E.leaf_total, d.G * d.Pmax, e->E.priors, e->E.values, d.Ap);
+      if (rc) return az_fail(rc, "network forward: " + g_az_error);
+#ifndef AZ_EMU
+      if (t == n_ticks - 1) cudaEventRecord(e->ev1, e->rt.stream);
+#endif
+      tree_pass(AZ_PH_APPLY | AZ_PH_ADVANCE | (t < n_ticks - 1 ? AZ_PH_COLLECT : 0));
+    }
+#ifndef AZ_EMU
+    cudaError_t fe = cudaGetLastError();
+    if (fe != cudaSuccess) return az_fail(AZ_ERR_CUDA, std::string("CUDA launch error: ") + cudaGetErrorString(fe));
+#endif
+    return AZ_OK;
+  }
   for (int t = 0; t < n_ticks; ++t) {
     AZ_PROF_MARK(0);
     launch_collect(e);
@@ -909,6 +991,70 @@ extern "C" int az_selfplay_tick(az_engine* e, int32_t n_ticks) {
   if (ce != cudaSuccess) return az_fail(AZ_ERR_CUDA, std::string("CUDA launch error: ") + cudaGetErrorString(ce));
 #endif
   return AZ_OK;
+}
+
+// ---- evaluation matches on the device (pipeline.py:815-867 for many games at once) ---------------------------------------
+extern "C" int az_match_begin(az_engine* e, const az_search_params* p, const uint8_t* black_net, int32_t games_per_slot, int32_t alternate) {
+  AZ_ENTER(e);
+  if (!e || !p) return az_fail(AZ_ERR_BAD_ARG, "null argument");
+  if (!e->net || !aznet_ready(e->net) || !e->net2 || !aznet_ready(e->net2))
+    return az_fail(AZ_ERR_STATE, "az_match_begin: both weight sets must be loaded (az_set_weights_for 0 and 1)");
+  if (games_per_slot < 1) return az_fail(AZ_ERR_BAD_ARG, "az_match_begin: games_per_slot must be positive");
+  int rc = set_search_cfg(e, p);
+  if (rc) return rc;
+  const AzDims& d = e->E.d;
+  AzSearchCfg& s = e->E.s;
+  s.selfplay = 1;
+  s.host_noise = 0;
+  s.warm_up_steps = -1;          // warm_up=False at every ply (pipeline.py:838)
+  s.check_resign_after = 1 << 30;
+  s.resign_threshold = -1.0f;    // no resignation in evaluation games
+  s.disable_resign_ratio = 1.0f;
+  s.match = 1;
+  s.match_games = games_per_slot;
+  s.match_alternate = alternate ? 1 : 0;
+  std::vector<uint8_t> bn((size_t)d.G, 0);
+  if (black_net)
+    for (int g = 0; g < d.G; ++g) bn[g] = black_net[g] ? 1 : 0;
+  rt_h2d(e->rt, e->E.slot_net, bn.data(), bn.size());
+  e->selfplay = true;
+  e->active.clear();
+  rt_zero(e->rt, e->E.counters, CT_COUNT * sizeof(unsigned long long));
+  e->drained_games = 0;
+  e->dropped_samples = 0;
+  AZ_LAUNCH_WARPS(e->rt, k_selfplay_begin, d.G, d, e->E);
+  return rt_sync(e->rt);
+}
+
+extern "C" int az_match_tick(az_engine* e, int32_t n_ticks, int32_t* n_running) {
+  AZ_ENTER(e);
+  if (!e) return az_fail(AZ_ERR_BAD_ARG, "null engine");
+  if (!e->selfplay || !e->E.s.match) return az_fail(AZ_ERR_STATE, "az_match_tick: call az_match_begin first");
+  const AzDims& d = e->E.d;
+  for (int t = 0; t < n_ticks; ++t) {
+    launch_collect(e);
+#ifdef AZ_EMU
+    k_compact_match(e->E, d.G);
+#else
+    k_compact_match<<<1, 1024, 0, e->rt.stream>>>(e->E, d.G);
+#endif
+    e->rt.launches++;
+    // each weight set evaluates the leaves of the games in which its colour is to move; rows are disjoint, outputs land in the same
+    // per-slot priors / values buffers
+    int rc = aznet_forward(e->net, e->rt, e->E.leaf_obs, e->E.leaf_rows, e->E.leaf_total, d.G * d.Pmax, e->E.priors, e->E.values, d.Ap);
+    if (!rc) rc = aznet_forward(e->net2, e->rt, e->E.leaf_obs, e->E.leaf_rows2, e->E.leaf_total + 4, d.G * d.Pmax, e->E.priors, e->E.values, d.Ap);
+    if (rc) return az_fail(rc, "network forward: " + g_az_error);
+    AZ_LAUNCH_WARPS(e->rt, k_apply, d.G, d, e->E);
+    AZ_LAUNCH_WARPS(e->rt, k_advance, d.G, d, e->E);
+  }
+  if (n_running) {
+    rt_zero(e->rt, e->d_out, sizeof(int32_t));
+    AZ_LAUNCH_THREADS(e->rt, k_count_active, d.G, e->E, e->d_out);
+    int32_t act = 0;
+    rt_d2h(e->rt, &act, e->d_out, sizeof(act));
+    *n_running = act;
+  }
+  return rt_sync(e->rt);
 }
 
 extern "C" int az_sync(az_engine* e) {

@@ -250,6 +250,18 @@ AZ_GLOBAL k_env_copy(AzState E, int src, int dst, int nwarps) {
   }
 }
 
+// number of slots still playing (match loop: slots retire after their games): out[0], zeroed by the first thread of the grid first
+AZ_GLOBAL k_count_active(AzState E, int32_t* out, int n) {
+#ifdef AZ_EMU
+  int c = 0;
+  for (int i = 0; i < n; ++i) c += E.tree_i[(size_t)i * TREE_INTS + TI_ACTIVE] ? 1 : 0;
+  out[0] = c;
+#else
+  // single CTA launch is not guaranteed by AZ_LAUNCH_THREADS: count with one atomic per thread that finds an active slot
+  AZ_THREAD_LOOP(i, n) if (E.tree_i[(size_t)i * TREE_INTS + TI_ACTIVE]) atomicAdd(out, 1);
+#endif
+}
+
 AZ_GLOBAL k_clear_active(AzState E, int n) {
   AZ_THREAD_LOOP(i, n) E.tree_i[(size_t)i * TREE_INTS + TI_ACTIVE] = 0;
 }
@@ -333,6 +345,72 @@ __global__ void k_compact(AzState E, int n) {  // one CTA of 1024 threads
 }
 #endif
 
+// Leaf-row compaction of the match loop: two lists, one per weight set (leaf_rows / leaf_total[0], leaf_rows2 / leaf_total[4]);
+// leaf_total[1] = running searches.  One CTA of 1024 threads, like k_compact.
+#ifdef AZ_EMU
+static void k_compact_match(AzState E, int n) {
+  int tot[2] = {0, 0}, running = 0;
+  for (int g = 0; g < n; ++g) {
+    const int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
+    const int c = ti[TI_ACTIVE] ? ti[TI_NLEAVES] : 0;
+    E.leaf_count[g] = c;
+    if (c) {
+      const int w = match_net_of(E, g);
+      int32_t* rows = w ? E.leaf_rows2 : E.leaf_rows;
+      for (int j = 0; j < c; ++j) rows[tot[w]++] = g * E.d.Pmax + j;
+    }
+    const int st = ti[TI_STATE];
+    if (ti[TI_ACTIVE] && (st == ST_NEED_ROOT || st == ST_SEARCH_INIT || st == ST_SEARCHING)) running++;
+  }
+  E.leaf_total[0] = tot[0];
+  E.leaf_total[1] = running;
+  E.leaf_total[4] = tot[1];
+}
+#else
+__global__ void __launch_bounds__(1024) k_compact_match(AzState E, int n) {
+  __shared__ int s_sum[2][1024];
+  __shared__ int s_run[32];
+  const int t = threadIdx.x;
+  const int per = (n + 1023) / 1024;
+  const int g0 = t * per, g1 = min(n, g0 + per);
+  int local[2] = {0, 0}, running = 0;
+  for (int g = g0; g < g1; ++g) {
+    const int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
+    const int c = ti[TI_ACTIVE] ? ti[TI_NLEAVES] : 0;
+    E.leaf_count[g] = c;
+    if (c) local[match_net_of(E, g)] += c;
+    const int st = ti[TI_STATE];
+    if (ti[TI_ACTIVE] && (st == ST_NEED_ROOT || st == ST_SEARCH_INIT || st == ST_SEARCHING)) running++;
+  }
+  s_sum[0][t] = local[0];
+  s_sum[1][t] = local[1];
+  running = w_sum_i(running);
+  if ((t & 31) == 0) s_run[t >> 5] = running;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan of both columns
+    const int v0 = t >= off ? s_sum[0][t - off] : 0, v1 = t >= off ? s_sum[1][t - off] : 0;
+    __syncthreads();
+    s_sum[0][t] += v0;
+    s_sum[1][t] += v1;
+    __syncthreads();
+  }
+  int pos[2] = {s_sum[0][t] - local[0], s_sum[1][t] - local[1]};
+  for (int g = g0; g < g1; ++g) {
+    const int c = E.leaf_count[g];
+    if (!c) continue;
+    const int w = match_net_of(E, g);
+    int32_t* rows = w ? E.leaf_rows2 : E.leaf_rows;
+    for (int j = 0; j < c; ++j) rows[pos[w]++] = g * E.d.Pmax + j;
+  }
+  if (t == 1023) { E.leaf_total[0] = s_sum[0][1023]; E.leaf_total[4] = s_sum[1][1023]; }
+  if (t == 0) {
+    int r = 0;
+    for (int k = 0; k < 32; ++k) r += s_run[k];
+    E.leaf_total[1] = r;
+  }
+}
+#endif
+
 // ---- slot-range kernels of the two-half pipeline (AZ_PIPELINE=1, az_engine.cu selfplay_tick_pipelined) ------------------
 // The games are split into two halves; while the network evaluates the leaves of one half on the engine stream, the tree
 // kernels of the other half run on a second stream.  Every kernel here is built for 7 CTAs per SM (<= 72 registers, 4 warps):
@@ -369,6 +447,54 @@ AZ_GLOBAL_R k_advance_r(AzState E, int g0, int nwarps) {
     game_advance(E, g0 + az_g, S);
   }
 }
+
+// Persistent fused tree pass of the slot range [g0, g0 + ng) (AZ_PIPELINE=2): games are independent and, per game, expand/backup ->
+// move/re-root -> leaf collection only depend on the game's own state, so ONE warp runs the requested phases of a game back to
+// back and then fetches the next game from a global counter.  The grid is at most one 4-warp CTA per SM: together with the <= 72
+// registers and 8 KB of scratch that is exactly what a persistent dense-x conv CTA leaves free on its SM, so this kernel is placed
+// beside the tensor-core kernel of the other half of the slots instead of queueing behind it (a 512-CTA launch fills the SMs
+// between two conv launches and starves the conv clusters: measured, profiles/r02_bench_go9_c2_n1_pipeline_v1.json).  The dynamic
+// distribution also takes the slowest games (late positions: 16 tries, 30-ply paths) off the critical path of a wave.
+#define AZ_PH_APPLY 1
+#define AZ_PH_ADVANCE 2
+#define AZ_PH_COLLECT 4
+#ifdef AZ_EMU
+static void k_tree_p(AzState E, int g0, int ng, int phases, unsigned int* ctr) {
+  for (int i = 0; i < ng; ++i) {
+    Sim S;
+    AZ_SCRATCH(E.d, S);
+    LocalCounters lc = {0, 0, 0, 0, 0, 0};
+    if (phases & AZ_PH_APPLY) game_apply(E, g0 + i, lc);
+    if (phases & AZ_PH_ADVANCE) game_advance(E, g0 + i, S);
+    if (phases & AZ_PH_COLLECT) game_collect_nc(E, g0 + i, S, lc);
+    flush_counters(E, lc);
+  }
+  (void)ctr;
+}
+#else
+__global__ void __launch_bounds__(AZ_WPB * 32, 7) k_tree_p(AzState E, int g0, int ng, int phases, unsigned int* ctr) {
+  Sim S;
+  AZ_SCRATCH(E.d, S);
+  LocalCounters lc = {0, 0, 0, 0, 0, 0};
+  for (bool first = true;; first = false) {
+    unsigned int i = 0;
+    if (ctr) {
+      if ((threadIdx.x & 31) == 0) i = atomicAdd(ctr, 1u);
+      i = __shfl_sync(0xffffffffu, i, 0);
+    } else {  // one game per warp, the grid covers the range (serial tick: a single wave)
+      if (!first) break;
+      i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    }
+    if (i >= (unsigned int)ng) break;
+    const int g = g0 + (int)i;
+    if (phases & AZ_PH_APPLY) game_apply(E, g, lc);
+    if (phases & AZ_PH_ADVANCE) game_advance(E, g, S);
+    if (phases & AZ_PH_COLLECT) game_collect_nc(E, g, S, lc);
+    __syncwarp();
+  }
+  flush_counters(E, lc);
+}
+#endif
 
 // Leaf-row compaction of the slots [g0, g0 + n): rows go to leaf_rows + g0 * Pmax, the totals to tot[0..1].
 #ifdef AZ_EMU

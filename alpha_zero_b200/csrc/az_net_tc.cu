@@ -862,20 +862,31 @@ k_conv_tc_x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       const int t = PAIR ? 2 * u + (int)crank : u;
       const long long tile_row0 = (long long)t * L.TH;
       const int acc = it & 1;
+      // which of this lane's two rows of the tile (h = 0, 1) hold an output: once per tile, in 32-bit arithmetic (the row index
+      // of the whole batch fits: checked at create), instead of a 64-bit modulo and a division in every pass
+      uint32_t vmask = 0;  // bit h: row h * 128 + q * 32 + lane of the tile holds an output
+      {
+        const uint32_t lrow = (uint32_t)(q * 32 + lane);
+        const uint32_t mrow = (uint32_t)tile_row0 + lrow;
+        const uint32_t r0 = mrow % (uint32_t)L.RP;
+        const uint32_t r1 = (r0 + 128u) % (uint32_t)L.RP;
+        const uint32_t hw = (uint32_t)(L.Hc * L.Hc);  // rows >= Hc*Hc of a leaf: its zero board row
+        if (lrow < (uint32_t)L.TH && (long long)mrow < M && r0 < hw) vmask |= 1u;
+        if (lrow + 128u < (uint32_t)L.TH && (long long)mrow + 128 < M && r1 < hw) vmask |= 2u;
+      }
       mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int ps = 0; ps < 2 * npass_c; ++ps) {
-        const int h = ps / npass_c, pc = ps - h * npass_c;
+        const int h = ps >= npass_c ? 1 : 0, pc = ps - h * npass_c;
         const int cc = col0 + pc * 32;
         const int l0 = h * 128 + q * 32;
         if constexpr (SPLIT) {
           // every lane owns one row: 64-byte segments of the hi / lo / hi column groups, read and written directly
           const int l = l0 + lane;
           const long long m = tile_row0 + l;
-          const int r = (int)(m % L.RP);
           const bool inb = (l < L.TH) && (m < M);
-          const bool valid = inb && (r / L.Hc) < L.Hc;
+          const bool valid = ((vmask >> h) & 1u) != 0;
           const size_t grow = ((size_t)L.guard + (size_t)(inb ? m : 0)) * L.ostride + cc;
           __align__(16) __nv_bfloat16 rh[32], rl[32];
           if (L.has_res && valid) {
@@ -915,17 +926,14 @@ k_conv_tc_x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stage + (size_t)(i * 8 + crow) * srow + cchunk * 16) = pre[i];
           const int nps = ps + 1;
           if (nps < 2 * npass_c) {
-            const int nh = nps / npass_c, npc = nps - nh * npass_c;
+            const int nh = nps >= npass_c ? 1 : 0, npc = nps - nh * npass_c;
             prefetch(tile_row0, nh * 128 + q * 32, col0 + npc * 32);
           } else if (u + ustep < num_units) {
             prefetch((long long)(t + tstep) * L.TH, q * 32, col0);
           }
         }
         __syncwarp();
-        const int l = l0 + lane;
-        const long long m = tile_row0 + l;
-        const int r = (int)(m % L.RP);
-        const bool valid = (l < L.TH) && (m < M) && (r / L.Hc) < L.Hc;  // the leaf's last board row is its zero row
+        const bool valid = ((vmask >> h) & 1u) != 0;
         unsigned char* myrow = stage + (size_t)lane * srow;
         {
           tc_wait_ld();
@@ -1030,6 +1038,10 @@ int aznet_tc_create(AzNet* n, AzRt& rt, std::string& err) {
   n->act_in = rt_alloc(n->rows_total * 64 * 2);
   if (!n->act_in) { err = "out of device memory"; return AZ_ERR_CUDA; }
   if (n->C != 64 && n->C != 128 && n->C != 256) { err = "tensor-core towers support num_filters <= 128 (padded to 64 / 128) or 193..256 (padded to 256)"; return AZ_ERR_BAD_ARG; }
+  if ((unsigned long long)n->max_leaves * (unsigned long long)n->g.RP + (unsigned long long)2 * n->g.guard >= (1ull << 31)) {
+    err = "tensor-core tower: leaf batch too large (row index must fit in 31 bits)";
+    return AZ_ERR_BAD_ARG;
+  }
   tc->split = n->precision == AZ_NET_BF16X3;
   const uint64_t CW = (uint64_t)(tc->split ? 3 * n->C : n->C);  // channels of a stored activation row
   int rc = make_map(&tc->map_in, n->act_in, 64, n->rows_total, TC_BM, err);

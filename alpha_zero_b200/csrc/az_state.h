@@ -83,6 +83,10 @@ struct AzSearchCfg {
   int warm_up_steps, check_resign_after;
   float resign_threshold, disable_resign_ratio;
   uint64_t seed;
+  // evaluation matches (pipeline.py:815-867): two weight sets, a fresh tree every move, a fixed number of games per slot
+  int match;            // 1: match loop (no subtree reuse, slot_net decides the evaluating network, slots retire after their games)
+  int match_games;      // games per slot
+  int match_alternate;  // 1: the networks swap colours from one game of a slot to the next
 };
 
 struct AzState {
@@ -117,6 +121,8 @@ struct AzState {
   int8_t* leaf_obs;
   float* priors;
   float* values;
+  int32_t* leaf_rows2;  // match loop: rows to be evaluated by the second weight set (leaf_total[4] of them)
+  uint8_t* slot_net;    // match loop: [G] which weight set (0 / 1) plays BLACK in the slot's first game
   int32_t* leaf_rows;   // compacted list of occupied rows g*Pmax+j
   int32_t* leaf_total;  // [0] number of occupied rows, [1] active searches
   int32_t* leaf_count;  // [G] leaves per slot of the last collect pass

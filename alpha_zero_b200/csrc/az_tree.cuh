@@ -107,21 +107,62 @@ AZ_DEV int tree_pick(const AzState& E, const TreeView& T, int g, int node, const
   const float* rP = T.P + (size_t)node * Ap;
   const int16_t* rC = T.cidx + (size_t)node * Ap;
   const double* p64 = E.root_p64 + (size_t)g * Ap;
-  double best = -1e300;
+  // The rows of a node are cold HBM lines, and a descent is a chain of such levels: all loads of a level are issued before the
+  // first value is consumed (PICK_CH elements per lane at a time), so a level costs one memory round trip instead of one per
+  // operand (ncu source view of the previous loop: 57 % of the kernel's stall samples sat on the first use of each row).
+  constexpr int PICK_CH = 3;
   int bi = 1 << 30, bc = -1;
   float bn = 0.f;
-  W_FOR(a, E.d.A) {
-    const float n_a = rN[a];
-    const int c_a = rC[a];
-    const float ratio = f_div(s32, f_add(1.0f, n_a));
-    const float q = f_div(rW[a], n_a > 0.f ? n_a : 1.0f);
-    double sc;
-    if (use64) sc = d_add((double)(-q), d_mul(d_mul(pbc, p64[a]), (double)ratio));
-    else sc = (double)f_add(-q, f_mul(f_mul(pbc32, rP[a]), ratio));
-    if (legal[a] != 1) sc = -9999.0;
-    if (sc > best) { best = sc; bi = a; bc = c_a; bn = n_a; }
+  if (!use64) {
+    float best = -INFINITY;
+    for (int a0 = 0; a0 < E.d.A; a0 += PICK_CH * AZ_WIDTH) {
+      float n_[PICK_CH], w_[PICK_CH], p_[PICK_CH];
+      int c_[PICK_CH], l_[PICK_CH];
+#pragma unroll
+      for (int k = 0; k < PICK_CH; ++k) {
+        const int a = a0 + k * AZ_WIDTH + AZ_LANE;
+        n_[k] = 0.f; w_[k] = 0.f; p_[k] = 0.f; c_[k] = -1; l_[k] = 0;
+        if (a < E.d.A) { n_[k] = rN[a]; c_[k] = rC[a]; w_[k] = rW[a]; p_[k] = rP[a]; l_[k] = legal[a]; }
+      }
+#pragma unroll
+      for (int k = 0; k < PICK_CH; ++k) {
+        const int a = a0 + k * AZ_WIDTH + AZ_LANE;
+        if (a < E.d.A) {
+          const float ratio = f_div(s32, f_add(1.0f, n_[k]));
+          const float q = f_div(w_[k], n_[k] > 0.f ? n_[k] : 1.0f);
+          float sc = f_add(-q, f_mul(f_mul(pbc32, p_[k]), ratio));
+          if (l_[k] != 1) sc = -9999.0f;
+          if (sc > best) { best = sc; bi = a; bc = c_[k]; bn = n_[k]; }
+        }
+      }
+    }
+    w_argmax_f(best, bi);
+  } else {
+    double best = -1e300;
+    for (int a0 = 0; a0 < E.d.A; a0 += PICK_CH * AZ_WIDTH) {
+      float n_[PICK_CH], w_[PICK_CH];
+      double p_[PICK_CH];
+      int c_[PICK_CH], l_[PICK_CH];
+#pragma unroll
+      for (int k = 0; k < PICK_CH; ++k) {
+        const int a = a0 + k * AZ_WIDTH + AZ_LANE;
+        n_[k] = 0.f; w_[k] = 0.f; p_[k] = 0.0; c_[k] = -1; l_[k] = 0;
+        if (a < E.d.A) { n_[k] = rN[a]; c_[k] = rC[a]; w_[k] = rW[a]; p_[k] = p64[a]; l_[k] = legal[a]; }
+      }
+#pragma unroll
+      for (int k = 0; k < PICK_CH; ++k) {
+        const int a = a0 + k * AZ_WIDTH + AZ_LANE;
+        if (a < E.d.A) {
+          const float ratio = f_div(s32, f_add(1.0f, n_[k]));
+          const float q = f_div(w_[k], n_[k] > 0.f ? n_[k] : 1.0f);
+          double sc = d_add((double)(-q), d_mul(d_mul(pbc, p_[k]), (double)ratio));
+          if (l_[k] != 1) sc = -9999.0;
+          if (sc > best) { best = sc; bi = a; bc = c_[k]; bn = n_[k]; }
+        }
+      }
+    }
+    w_argmax(best, bi);
   }
-  w_argmax(best, bi);
   // the winner is the local best of the lane that owns it (same tie-break locally and globally)
   child_link = w_bcast_i(bc, bi);
   n_child = w_bcast_f(bn, bi);
@@ -572,6 +613,7 @@ AZ_DEV void game_apply(const AzState& E, int g, LocalCounters& lc) {
   const float* pri = E.priors + (size_t)g * d.Pmax * d.Ap;
   const float* val = E.values + (size_t)g * d.Pmax;
   if (st == ST_NEED_ROOT) {
+    if (ti[TI_NLEAVES] < 1) return;  // no root evaluation collected yet (freshly begun / restarted slot in a fused apply-first pass)
     tree_init_node(E, T, 0, -1, -1, E.env_i[(size_t)g * ENV_INTS + EI_TO_PLAY]);
     W_LANE0 {
       ti[TI_NODES] = 1;
@@ -750,6 +792,7 @@ AZ_DEV void game_new(const AzState& E, int g, Sim& S) {
     ti[TI_GAME_PLY] = 0;
     ti[TI_MARKED] = 0;
     ti[TI_NODES] = 0;
+    ti[TI_NLEAVES] = 0;  // leaves of the previous game (already consumed, or abandoned by a restart) are not this game's
     ti[TI_STATE] = ST_NEED_ROOT;
     ti[TI_WARM] = (0 <= E.s.warm_up_steps) ? 1 : 0;
     // resign lottery (pipeline.py:244-246)
@@ -825,7 +868,8 @@ AZ_DEV void game_advance(const AzState& E, int g, Sim& S) {
   if (!o.done) {
     W_LANE0 ti[TI_WARM] = (ei[EI_STEPS] <= E.s.warm_up_steps) ? 1 : 0;
     w_sync();
-    const int kept = game_commit(E, g, play, nullptr);
+    // evaluation matches search every move from a fresh root (`root_node=None`, pipeline.py:834-840): the tree is dropped
+    const int kept = E.s.match ? 0 : game_commit(E, g, play, nullptr);
     if (kept) {
       W_LANE0 ti[TI_STATE] = ST_SEARCH_INIT;
       w_sync();
@@ -890,5 +934,19 @@ AZ_DEV void game_advance(const AzState& E, int g, Sim& S) {
     atomic_add_u64(&E.counters[CT_SAMPLES], (unsigned long long)len);
   }
   w_sync();
+  if (E.s.match && ti[TI_SLOT_GAMES] >= E.s.match_games) {  // the slot has played its games: retire it
+    W_LANE0 { ti[TI_ACTIVE] = 0; ti[TI_STATE] = ST_IDLE; ti[TI_NLEAVES] = 0; }
+    w_sync();
+    return;
+  }
   game_new(E, g, S);
+}
+
+// Which weight set evaluates the leaves of slot g in the match loop: the one that plays the colour to move at the ROOT (each
+// player searches with its own network, also below opponent nodes of its tree: pipeline.py:826-840).
+AZ_DEV int match_net_of(const AzState& E, int g) {
+  const int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
+  int black_net = E.slot_net[g];
+  if (E.s.match_alternate) black_net ^= (ti[TI_SLOT_GAMES] - 1) & 1;
+  return E.env_i[(size_t)g * ENV_INTS + EI_TO_PLAY] == 1 ? black_net : 1 - black_net;
 }

@@ -27,6 +27,7 @@ AZ_DEV int w_min_i(int v) { return v; }
 AZ_DEV double w_sum_d(double v) { return v; }
 AZ_DEV float w_sum_f(float v) { return v; }
 AZ_DEV void w_argmax(double& v, int& i) { (void)v; (void)i; }
+AZ_DEV void w_argmax_f(float& v, int& i) { (void)v; (void)i; }
 AZ_DEV int w_bcast_i(int v, int) { return v; }
 AZ_DEV float w_bcast_f(float v, int) { return v; }
 AZ_DEV float f_mul(float a, float b) { return a * b; }  // built with -ffp-contract=off
@@ -76,6 +77,17 @@ AZ_DEV void w_argmax(double& v, int& i) {
     int oi = __shfl_xor_sync(AZ_FULL, i, o);
     if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
   }
+}
+// The same for float32 scores (every level below a noised root) in two warp reductions instead of fifteen shuffles: the maximum
+// of an order-preserving integer image of the scores (redux.sync.max), then the lowest index among the lanes that hold it
+// (redux.sync.min).  A lane's (v, i) is its local best with the lowest-index tie-break already applied; v is never NaN.
+AZ_DEV void w_argmax_f(float& v, int& i) {
+  const uint32_t b = __float_as_uint(v);
+  const uint32_t key = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  const uint32_t top = __reduce_max_sync(AZ_FULL, key);
+  i = (int)__reduce_min_sync(AZ_FULL, key == top ? (uint32_t)i : 0xffffffffu);
+  const uint32_t tb = (top & 0x80000000u) ? (top & 0x7fffffffu) : ~top;
+  v = __uint_as_float(tb);
 }
 AZ_DEV int w_bcast_i(int v, int src) { return __shfl_sync(AZ_FULL, v, src & 31); }
 AZ_DEV float w_bcast_f(float v, int src) { return __shfl_sync(AZ_FULL, v, src & 31); }

@@ -69,6 +69,13 @@ class Engine:
         self.b.check(self.b.dll.az_set_weights(self.h, ptrs, numel, len(ts)))
         self.weight_bytes = int(sum(t.nbytes for t in ts))
 
+    def set_weights_for(self, which, state_dict):
+        """Weight set 0 (== set_weights) or 1 (the opponent of an evaluation match)."""
+        ts = state_dict_tensors(state_dict)
+        ptrs = (C.POINTER(C.c_float) * len(ts))(*[as_ptr(t, C.c_float) for t in ts])
+        numel = (C.c_int64 * len(ts))(*[t.size for t in ts])
+        self.b.check(self.b.dll.az_set_weights_for(self.h, int(which), ptrs, numel, len(ts)))
+
     def net_forward(self, obs):
         obs = np.ascontiguousarray(obs, dtype=np.int8).reshape(-1, self.obs_bytes)
         n = obs.shape[0]
@@ -236,6 +243,18 @@ class Engine:
         s = i32(slots).ravel()
         if s.size:
             self.b.check(self.b.dll.az_selfplay_restart(self.h, as_ptr(s, C.c_int32), s.size))
+
+    def match_begin(self, num_simulations, num_parallel, c_puct_base=19652.0, c_puct_init=1.25, black_net=None, games_per_slot=1, alternate=False,
+                    deterministic=False):
+        """Arm the device-resident match loop: weight set 0 vs weight set 1 in every slot (az_match_begin)."""
+        p = AzSearchParams(c_puct_base, c_puct_init, int(num_simulations), int(num_parallel), 0, int(bool(deterministic)))
+        bn = None if black_net is None else np.ascontiguousarray(black_net, dtype=np.uint8).reshape(self.G)
+        self.b.check(self.b.dll.az_match_begin(self.h, C.byref(p), as_ptr(bn, C.c_uint8) if bn is not None else None, int(games_per_slot), int(bool(alternate))))
+
+    def match_tick(self, n=1):
+        run = C.c_int32()
+        self.b.check(self.b.dll.az_match_tick(self.h, int(n), C.byref(run)))
+        return int(run.value)
 
     def selfplay_tick(self, n=1):
         self.b.check(self.b.dll.az_selfplay_tick(self.h, int(n)))

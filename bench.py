@@ -302,7 +302,9 @@ def short_run(game, n, G, sims, par, net_dims, sd, precision, warm, chk, resign,
 
     eng = Engine(game, n, num_games=G, max_simulations=sims, max_parallel=par, net=net_dims, precision=precision, device=device, seed=seed)
     eng.set_weights(sd)
-    eng.selfplay_begin(par, par, warm_up_steps=warm, check_resign_after_steps=chk, resign_threshold=-1.0, disable_resign_ratio=1.0)
+    # the resign lottery of a game is drawn when it starts (pipeline.py:244-246): the prologue runs under the workload's threshold
+    # and ratio, with the resign CHECK pushed out of reach, so that the aged population has the workload's mix of resign-enabled games
+    eng.selfplay_begin(par, par, warm_up_steps=warm, check_resign_after_steps=1 << 20, resign_threshold=resign[0], disable_resign_ratio=resign[1])
     stagger_population(eng, G, L, par, warm, chk, sims, resign)
     stream = stream_of(eng)
     for _ in range(warmup):
@@ -397,7 +399,7 @@ def main():
     stream = stream_of(eng)
     L = 0 if a.cold_start else min(STAGGER[a.workload], max(1, G))
     if L:
-        eng.selfplay_begin(par, par, warm_up_steps=warm, check_resign_after_steps=chk, resign_threshold=-1.0, disable_resign_ratio=1.0)
+        eng.selfplay_begin(par, par, warm_up_steps=warm, check_resign_after_steps=1 << 20, resign_threshold=resign[0], disable_resign_ratio=resign[1])
         stagger_population(eng, G, L, par, warm, chk, sims, resign)
     else:
         eng.selfplay_begin(sims, par, warm_up_steps=warm, check_resign_after_steps=chk, resign_threshold=resign[0], disable_resign_ratio=resign[1])

@@ -127,6 +127,10 @@ int az_obs_bytes(az_engine* e);              /* (2*num_stack+1)*N*N int8, envs/b
  * 232-239). */
 int az_set_weights(az_engine* e, const float* const* tensors, const int64_t* numel, int32_t n_tensors);
 
+/* Second weight set of the engine (which = 1; which = 0 is az_set_weights): the opponent of an evaluation match
+ * (run_evaluator_loop keeps `network` and `prev_ckpt_network`, core/pipeline.py:722-757). */
+int az_set_weights_for(az_engine* e, int32_t which, const float* const* tensors, const int64_t* numel, int32_t n_tensors);
+
 /* Network forward on host observations (eval_position, core/pipeline.py:91-123):
  * obs int8 [n, 2*num_stack+1, N, N] -> priors float32 [n, A] (softmax over ALL actions), values float32 [n]. */
 int az_net_forward(az_engine* e, const int8_t* obs, int32_t n, float* priors, float* values);
@@ -205,6 +209,15 @@ int az_selfplay_update(az_engine* e, const az_selfplay_params* p);
  * (training_go.py:318-330 spawns them, core/pipeline.py:227 is their game loop).  Must be called between ticks.  bench.py
  * uses it once to stagger the ages of a freshly begun population so that the timed window sees games finishing. */
 int az_selfplay_restart(az_engine* e, const int32_t* slots, int32_t n);
+/* ---- evaluation matches on the device: eval_against_prev_ckpt (core/pipeline.py:815-867) and
+ * eval_play/eval_agent_go_mass_matches.py:103-146 for every slot at once.  Weight set 0 against weight set 1, a fresh search tree
+ * every move (root_node=None), no root noise, warm_up=False, no resignation; each player's search is evaluated by its own network.
+ * black_net[g] (0 / 1, NULL = all 0) is the weight set that plays black in slot g's first game; with `alternate` the colours swap
+ * from one game of a slot to the next; a slot retires after games_per_slot games.  az_match_tick runs n leaf batches for every
+ * running game and reports how many slots are still playing; finished games come back through az_drain_games (record.reserved =
+ * games_started_before_in_slot * num_games + slot, so the colours of a record follow from black_net / alternate). */
+int az_match_begin(az_engine* e, const az_search_params* p, const uint8_t* black_net, int32_t games_per_slot, int32_t alternate);
+int az_match_tick(az_engine* e, int32_t n_ticks, int32_t* n_running);
 int az_sync(az_engine* e);
 int az_get_counters(az_engine* e, az_counters* out);
 /* Drain finished games: up to max_games records and their samples, oldest first.

@@ -246,3 +246,52 @@ def batched_matches(game):
             assert env.legal_actions[mv] == 1
             env.step(mv)
         assert env.is_game_over() and env.get_result_string() == g['game_result'] and env.steps == g['game_length']
+
+
+def device_matches(game, binding=None, on_gpu=False):
+    """play_matches_on_device (both weight sets in one engine, the loop on the device: az_match_begin / az_match_tick).
+    Every game is a legal, finished game whose result string equals an oracle replay; games are numbered and coloured as
+    documented (odd games swapped); deterministic games repeat exactly.  On the GPU the deterministic match must also equal the
+    host-driven play_matches (split-phase search + az_net_forward of each network) move for move, in both colour assignments."""
+    import torch
+
+    from alpha_zero_b200.matches import play_matches, play_matches_on_device
+    from alpha_zero_b200.network import AlphaZeroNet, randomize_batchnorm
+    from oracle.boards import GoBoard, GomokuBoard
+
+    kind, n, A = ('go', 9, 82) if game == 'go9' else ('gomoku', 13, 169)
+    dims = (2, 64, 64) if on_gpu else (1, 16, 16)
+    nets = []
+    for seed in (11, 12):
+        torch.manual_seed(seed)
+        nets.append(randomize_batchnorm(AlphaZeroNet((17, n, n), A, *dims, kind == 'gomoku'), seed=seed).eval())
+    kw = dict(num_simulations=24, num_parallel=4, max_steps=30 if kind == 'go' else 0, binding=binding, precision='fp32')
+
+    def replay(g):
+        env = GoBoard(9, 7.5, 8, 30) if kind == 'go' else GomokuBoard(13, 5, 8)
+        for mv in g['moves']:
+            assert env.legal_actions[mv] == 1
+            env.step(mv)
+        assert env.is_game_over() and env.get_result_string() == g['game_result'] and env.steps == g['game_length']
+
+    # 7 games on 3 slots: three rounds per slot, odd slot count -> colours alternate inside a slot
+    many = play_matches_on_device(7, kind, n, nets[0], nets[1], swap_colours=True, slots=3, seed=5, **kw)
+    assert [g['game'] for g in many] == list(range(7))
+    assert [g['black_is'] for g in many] == ['black', 'white'] * 3 + ['black']
+    for g in many:
+        replay(g)
+    assert len({tuple(g['moves']) for g in many}) > 1  # sampled games differ
+    assert many[0]['engine_counters']['simulations'] > 0
+    det = play_matches_on_device(4, kind, n, nets[0], nets[1], swap_colours=True, slots=4, deterministic=True, **kw)
+    assert det[0]['moves'] == det[2]['moves'] and det[1]['moves'] == det[3]['moves']
+    for g in det:
+        replay(g)
+    if on_gpu:
+        os.environ['AZ_NET_PRECISION'] = 'fp32'
+        try:
+            host = play_matches(1, kind, n, nets[0], nets[1], num_simulations=24, num_parallel=4, max_steps=30 if kind == 'go' else 0, deterministic=True)
+            host_swapped = play_matches(1, kind, n, nets[1], nets[0], num_simulations=24, num_parallel=4, max_steps=30 if kind == 'go' else 0, deterministic=True)
+        finally:
+            os.environ.pop('AZ_NET_PRECISION', None)
+        assert det[0]['moves'] == host[0]['moves'] and det[0]['game_result'] == host[0]['game_result']
+        assert det[1]['moves'] == host_swapped[0]['moves'] and det[1]['game_result'] == host_swapped[0]['game_result']

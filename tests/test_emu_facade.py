@@ -39,3 +39,10 @@ def test_error_paths():
 @pytest.mark.parametrize('game', ['go9', 'gomoku13'])
 def test_batched_matches(game):
     facadecheck.batched_matches(game)
+
+
+@pytest.mark.parametrize('game', ['go9', 'gomoku13'])
+def test_device_matches(game):
+    from alpha_zero_b200.envs import _pool
+
+    facadecheck.device_matches(game, binding=_pool._TEST_BINDING)

@@ -87,7 +87,7 @@ def test_reference_traces_in_every_variant(libs, node_cache_env, variant, nc, ga
 
 def _games_by_uid(binding, pipeline, game, ticks_per_call):
     """Self-play on 10 slots; every finished game keyed by its uid -> digest of (record, states, pi, z, moves)."""
-    os.environ['AZ_PIPELINE'] = '1' if pipeline else '0'
+    os.environ['AZ_PIPELINE'] = str(int(pipeline))
     try:
         n, A = 9, (82 if game == 'go' else 81)
         eng = Engine(game, n, num_games=10, max_simulations=32, max_parallel=4, net=(1, 16, 16), precision='fp32', seed=33, max_steps=50 if game == 'go' else 0,
@@ -129,6 +129,7 @@ def test_two_half_pipeline_plays_the_same_games(libs, node_cache_env, game):
     node_cache_env(1)
     ref = _games_by_uid(libs[''], False, game, 7)
     assert len(ref[0]) >= 8
-    for ticks_per_call in (7, 1, 20):
-        got = _games_by_uid(libs[''], True, game, ticks_per_call)
-        assert got == ref, (ticks_per_call, got[2], ref[2])
+    for mode in (1, 2):  # 2 = persistent fused tree pass: expand/backup -> move -> collection of a game back to back in one warp
+        for ticks_per_call in (7, 1, 20):
+            got = _games_by_uid(libs[''], mode, game, ticks_per_call)
+            assert got == ref, (mode, ticks_per_call, got[2], ref[2])

@@ -44,6 +44,11 @@ def test_batched_matches(game):
     facadecheck.batched_matches(game)
 
 
+@pytest.mark.parametrize('game', ['go9', 'gomoku13'])
+def test_device_matches(game):
+    facadecheck.device_matches(game, on_gpu=True)
+
+
 def test_create_mcts_player_matches_oracle_game():
     """create_mcts_player(network, device, ...) + play_and_record_one_game with the CUDA fp32 tower vs the oracle game loop with
     the torch fp32 net under the same numpy seed: identical move history and z, pi within 1e-3."""

@@ -64,3 +64,23 @@ dt = time.perf_counter() - t0
 moves = sum(r['game_length'] for r in res)
 print(json.dumps({'metric': 'evaluation_match_simulations_per_sec', 'games': len(res), 'moves': moves, 'value': moves * 100 / dt, 'seconds': dt,
                   'black_wins': sum(r['winner'] == 'B' for r in res), 'note': 'lock-step games, leaves of all games in one batch per network call, host hop'}))
+
+# the same matches with both weight sets in ONE engine and the loop on the device (az_match_begin / az_match_tick): the trained
+# checkpoint against a random-init net when the checkpoint fixture is present, 400 simulations, games capped at 40 plies
+from alpha_zero_b200.matches import play_matches_on_device
+
+ck = os.path.join('tests', 'golden', 'ckpt_go9_154000.npz')
+if os.path.exists(ck):
+    w = np.load(ck)
+    black.load_state_dict({k: torch.from_numpy(w[k]) for k in w.files if k != 'versions'})
+for n_games, slots, sims in ((1024, 1024, 400), (4096, 4096, 400)):
+    t0 = time.perf_counter()
+    res = play_matches_on_device(n_games, 'go', 9, black, white, torch.device('cuda:0'), num_simulations=sims, num_parallel=8, swap_colours=True, slots=slots,
+                                 precision='bf16', max_steps=40)
+    dt = time.perf_counter() - t0
+    c = res[0]['engine_counters']
+    first_wins = sum((r['winner'] == 'B') == (r['black_is'] == 'black') and r['winner'] is not None for r in res)
+    print(json.dumps({'metric': 'evaluation_match_simulations_per_sec', 'impl': 'device loop, two weight sets in one engine', 'games': len(res), 'slots': slots,
+                      'moves': c['moves'], 'value': c['simulations'] / dt, 'seconds': dt, 'games_per_sec': len(res) / dt,
+                      'mean_game_length': sum(r['game_length'] for r in res) / len(res), 'first_network_wins': first_wins,
+                      'note': 'wall clock incl. engine creation and weight upload; games capped at 40 plies; fresh tree every move, no noise, T=0.1 sampling on the device'}))
