@@ -48,6 +48,8 @@ struct az_engine {
   // az_tick_profile: per-phase device time of the self-play tick, CUDA events on the engine stream
   // AZ_PIPELINE=1 (opt-in): two halves of the slots; the tree kernels of one half run on `tree_rt` while the network evaluates
   // the other half on `rt`
+  bool defer_reroot = true;         // AZ_DEFER_REROOT (default 1): k_advance_d + k_reroot_payload instead of the one-warp re-root
+  int payload_ctas = 592;
   bool fused_tree = false;          // AZ_FUSED_TREE=1: serial tick with the fused apply -> advance -> collect pass (measured: no gain, off)
   bool pipeline = false;
   int pipeline_mode = 0;            // 1: one launch per phase, 512-CTA grids; 2: persistent fused tree pass, <= one CTA per SM
@@ -65,6 +67,20 @@ struct az_engine {
   int prof_pending = 0;                 // ticks recorded and not yet folded into prof_ms
 #endif
 };
+
+// move / re-root / game end of every slot whose search is complete; the payload of the re-roots is spread over the grid
+static void launch_advance(az_engine* e) {
+  const AzDims& d = e->E.d;
+  if (!e->defer_reroot) { AZ_LAUNCH_WARPS(e->rt, k_advance, d.G, d, e->E); return; }
+  rt_zero(e->rt, e->E.rr_count, sizeof(int32_t));
+  AZ_LAUNCH_WARPS(e->rt, k_advance_d, d.G, d, e->E);
+#ifdef AZ_EMU
+  k_reroot_payload(e->E, 0);
+#else
+  k_reroot_payload<<<e->payload_ctas, AZ_WPB * 32, 0, e->rt.stream>>>(e->E, 0);
+#endif
+  e->rt.launches++;
+}
 
 static void launch_collect(az_engine* e) {
   const AzDims& d = e->E.d;
@@ -220,6 +236,8 @@ extern "C" int az_create(const az_config* cfg, az_engine** out) {
   E.root_p64 = dev_alloc<double>(e, G * d.Ap);
   E.noise = dev_alloc<double>(e, G * d.Ap);
   E.remap = dev_alloc<int16_t>(e, G * d.cap);
+  E.rr_jobs = dev_alloc<int32_t>(e, G);
+  E.rr_count = dev_alloc<int32_t>(e, 1);
   {
     // per-node position cache (one ply per descent instead of a replay from the root): AZ_NODE_CACHE=0 switches it off
     const char* nc = getenv("AZ_NODE_CACHE");
@@ -288,6 +306,15 @@ extern "C" int az_create(const az_config* cfg, az_engine** out) {
     e->collect_occ = oc ? atoi(oc) != 0 : e->E.d.node_cache != 0;
   }
 #endif
+  {
+    const char* dr = getenv("AZ_DEFER_REROOT");
+    e->defer_reroot = dr ? atoi(dr) != 0 : true;
+#ifndef AZ_EMU
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->rt.device);
+    e->payload_ctas = sms * 4;
+#endif
+  }
   {
     const char* ft = getenv("AZ_FUSED_TREE");
     e->fused_tree = ft ? atoi(ft) != 0 : false;
@@ -977,7 +1004,7 @@ extern "C" int az_selfplay_tick(az_engine* e, int32_t n_ticks) {
     AZ_PROF_MARK(2);
     AZ_LAUNCH_WARPS(e->rt, k_apply, d.G, d, e->E);
     AZ_PROF_MARK(3);
-    AZ_LAUNCH_WARPS(e->rt, k_advance, d.G, d, e->E);
+    launch_advance(e);
     AZ_PROF_MARK(4);
   }
 #undef AZ_PROF_MARK
@@ -1045,7 +1072,7 @@ extern "C" int az_match_tick(az_engine* e, int32_t n_ticks, int32_t* n_running) 
     if (!rc) rc = aznet_forward(e->net2, e->rt, e->E.leaf_obs, e->E.leaf_rows2, e->E.leaf_total + 4, d.G * d.Pmax, e->E.priors, e->E.values, d.Ap);
     if (rc) return az_fail(rc, "network forward: " + g_az_error);
     AZ_LAUNCH_WARPS(e->rt, k_apply, d.G, d, e->E);
-    AZ_LAUNCH_WARPS(e->rt, k_advance, d.G, d, e->E);
+    launch_advance(e);
   }
   if (n_running) {
     rt_zero(e->rt, e->d_out, sizeof(int32_t));

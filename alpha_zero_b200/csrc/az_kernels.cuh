@@ -122,6 +122,25 @@ AZ_GLOBAL k_advance(AzState E, int nwarps) {
   }
 }
 
+// Self-play tick: the few games that move in a tick (one in ~50) each re-root a subtree of some hundred nodes; done by their own
+// warp alone that serial copy is the kernel's duration.  k_advance_d copies the new root only and queues the slot; k_reroot_payload
+// (launched right behind it) spreads the remaining nodes of all queued slots over the whole grid.
+AZ_GLOBAL k_advance_d(AzState E, int nwarps) {
+  AZ_WARP_INDEX(nwarps) {
+    Sim S;
+    AZ_SCRATCH(E.d, S);
+    game_advance(E, az_g, S, true);
+  }
+}
+
+#ifdef AZ_EMU
+static void k_reroot_payload(AzState E, int) { reroot_payload(E, 0, 1); }
+#else
+__global__ void __launch_bounds__(AZ_WPB * 32) k_reroot_payload(AzState E, int) {
+  reroot_payload(E, blockIdx.x * (blockDim.x >> 5) + (int)(threadIdx.x >> 5), gridDim.x * (blockDim.x >> 5));
+}
+#endif
+
 AZ_GLOBAL k_selfplay_begin(AzState E, int nwarps) {
   AZ_WARP_INDEX(nwarps) {
     Sim S;

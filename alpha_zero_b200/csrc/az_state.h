@@ -108,6 +108,8 @@ struct AzState {
   double* root_p64;
   double* noise;       // [G][Ap] host-supplied Dirichlet samples
   int16_t* remap;      // [G][cap]
+  int32_t* rr_jobs;    // [G] slots whose re-root left nodes 1.. of the payload to k_reroot_payload
+  int32_t* rr_count;   // [1] number of such jobs of the current k_advance launch
   // per-node position cache (d.node_cache): the position AFTER the move that leads to the node, written when the node is first
   // reached as a leaf; interior levels of a descent read the legal mask from here instead of replaying the game from the root
   int8_t* nboard;      // [G][2][cap][ncp]

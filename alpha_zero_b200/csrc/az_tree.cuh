@@ -135,6 +135,28 @@ AZ_DEV int tree_pick(const AzState& E, const TreeView& T, int g, int node, const
           if (sc > best) { best = sc; bi = a; bc = c_[k]; bn = n_[k]; }
         }
       }
+#ifndef AZ_EMU
+      // Hint: while the scores are reduced, pull the rows of the most-visited expanded child towards L2 - PUCT picks it more often
+      // than not, and the next level then starts on warm lines.  Results never depend on it.
+      if (a0 == 0 && T.nboard != nullptr) {
+        uint32_t nk = 0;
+        int ck = -1;
+#pragma unroll
+        for (int k = 0; k < PICK_CH; ++k)
+          if ((c_[k] & AZ_CIDX_EXPANDED) && c_[k] >= 0 && __float_as_uint(n_[k]) >= nk) { nk = __float_as_uint(n_[k]); ck = c_[k] & AZ_CIDX_MASK; }
+        const uint32_t top = __reduce_max_sync(AZ_FULL, ck >= 0 ? nk : 0u);
+        const uint32_t who = __ballot_sync(AZ_FULL, ck >= 0 && nk == top);
+        if (who) {
+          const int pc = __shfl_sync(AZ_FULL, ck, __ffs(who) - 1);
+          const size_t po = (size_t)pc * Ap;
+          w_prefetch(T.N + po, Ap * 4);
+          w_prefetch(T.W + po, Ap * 4);
+          w_prefetch(T.P + po, Ap * 4);
+          w_prefetch(T.cidx + po, Ap * 2);
+          w_prefetch(T.nlegal + po, Ap);
+        }
+      }
+#endif
     }
     w_argmax_f(best, bi);
   } else {
@@ -458,27 +480,37 @@ AZ_DEV void game_collect(const AzState& E, int g, Sim& S, LocalCounters& lc) {
 // board of the path node at depth-k, or - past the root - the slot's own history (envs/base.py:243-261).
 AZ_DEV void leaf_write_obs(const AzState& E, const TreeView& T, int g, const Sim& S, int node, int depth, int8_t* out) {
   const AzDims& d = E.d;
+  // the num_stack source boards first (scratch, cached boards of the path nodes, the slot's history: cold global lines), all loads
+  // of a chunk of cells in flight together, then the 2 * num_stack + 1 planes
+  const int8_t* src[8];
   int anc = node;  // node at depth - k while walking up (only used when the path was too deep to be recorded)
-  for (int k = 0; k < d.num_stack; ++k) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
     const int j = depth - k;
-    const int8_t* b;
-    if (k == 0) b = S.board;
-    else if (j >= 1) {
-      if (depth <= AZ_PATH) anc = S.path_n[j - 1];
-      else anc = T.parent[anc];
-      b = T.nboard + (size_t)anc * d.ncp;
-    } else b = E.hist + ((size_t)g * 8 + (size_t)(-j)) * d.ncp;
-    int8_t* o0 = out + (size_t)(2 * k) * d.nc;
-    int8_t* o1 = o0 + d.nc;
-    W_FOR(c, d.nc) {
-      const int8_t v = b[c];
-      o0[c] = (v == S.to_play);
-      o1[c] = (v == -S.to_play);
+    src[k] = S.board;
+    if (k > 0 && k < d.num_stack) {
+      if (j >= 1) {
+        if (depth <= AZ_PATH) anc = S.path_n[j - 1];
+        else anc = T.parent[anc];
+        src[k] = T.nboard + (size_t)anc * d.ncp;
+      } else src[k] = E.hist + ((size_t)g * 8 + (size_t)(-j)) * d.ncp;
     }
   }
-  int8_t* oc = out + (size_t)(2 * d.num_stack) * d.nc;
+  const int8_t me = (int8_t)S.to_play, opp = (int8_t)(-S.to_play);
   const int8_t colour = (S.to_play == 1);
-  W_FOR(c, d.nc) oc[c] = colour;
+  for (int c = AZ_LANE; c < d.nc; c += AZ_WIDTH) {
+    int8_t v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = k < d.num_stack ? src[k][c] : (int8_t)0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k < d.num_stack) {
+        out[(size_t)(2 * k) * d.nc + c] = (v[k] == me);
+        out[(size_t)(2 * k + 1) * d.nc + c] = (v[k] == opp);
+      }
+    }
+    out[(size_t)(2 * d.num_stack) * d.nc + c] = colour;
+  }
   w_sync();
 }
 
@@ -656,7 +688,81 @@ AZ_DEV void game_apply(const AzState& E, int g, LocalCounters& lc) {
 
 // Re-root on `move` (mcts_v2.py:643-653): the subtree of the chosen child is compacted breadth-first
 // into the slot's other node pool; siblings are dropped.  Returns 1 if a subtree was kept.
-AZ_DEV int game_commit(const AzState& E, int g, int move, double* best_child_q) {
+// payload of one kept node: old index `old` of the source pool -> index `i` of the destination pool; all loads before the first store
+AZ_DEV void commit_copy_node(const TreeView& To, TreeView& Tn, size_t old, int i, int Ap, int ncp) {
+  constexpr int KC = 3;
+  const bool cache = To.nboard != nullptr;
+  const uint8_t ex = To.expanded[old];
+  const int8_t tp = To.to_play[old];
+  const int16_t ko = cache ? To.nko[old] : (int16_t)-1;
+  for (int a00 = 0; a00 < Ap; a00 += KC * AZ_WIDTH) {
+    float fn[KC], fw[KC], fp[KC];
+    uint8_t lg[KC];
+    int8_t bd[KC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      const int a = a00 + k * AZ_WIDTH + AZ_LANE;
+      fn[k] = fw[k] = fp[k] = 0.f; lg[k] = 0; bd[k] = 0;
+      if (a < Ap) {
+        fn[k] = To.N[old * Ap + a];
+        fw[k] = To.W[old * Ap + a];
+        fp[k] = To.P[old * Ap + a];
+        if (cache) {
+          lg[k] = To.nlegal[old * Ap + a];
+          if (a < ncp) bd[k] = To.nboard[old * ncp + a];
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      const int a = a00 + k * AZ_WIDTH + AZ_LANE;
+      if (a < Ap) {
+        Tn.N[(size_t)i * Ap + a] = fn[k];
+        Tn.W[(size_t)i * Ap + a] = fw[k];
+        Tn.P[(size_t)i * Ap + a] = fp[k];
+        if (cache) {
+          Tn.nlegal[(size_t)i * Ap + a] = lg[k];
+          if (a < ncp) Tn.nboard[(size_t)i * ncp + a] = bd[k];
+        }
+      }
+    }
+  }
+  W_LANE0 {
+    Tn.expanded[i] = ex;
+    Tn.to_play[i] = tp;
+    Tn.vloss[i] = 0;
+    if (cache) Tn.nko[i] = ko;
+  }
+}
+
+AZ_DEV void commit_prefetch_node(const TreeView& To, size_t pf, int Ap, int ncp) {
+  w_prefetch(To.N + pf * Ap, Ap * 4);
+  w_prefetch(To.W + pf * Ap, Ap * 4);
+  w_prefetch(To.P + pf * Ap, Ap * 4);
+  if (To.nboard != nullptr) { w_prefetch(To.nboard + pf * ncp, ncp); w_prefetch(To.nlegal + pf * Ap, Ap); }
+}
+
+// Deferred payload of the re-roots of one k_advance launch (jobs in E.rr_jobs[0 .. *E.rr_count)): `per` consecutive warps of the
+// grid share one job and stride over its nodes 1 .. count-1 (node 0 was copied by the advancing warp).  TI_BUF already names the
+// destination pool; the old indices are still in the slot's remap table.
+AZ_DEV void reroot_payload(const AzState& E, int warp_global, int total_warps) {
+  const int n_jobs = *E.rr_count;
+  if (n_jobs <= 0) return;
+  const int per = total_warps / n_jobs > 1 ? total_warps / n_jobs : 1;
+  const int lanes_of_jobs = total_warps / per;  // jobs served per sweep
+  const int r = warp_global % per;
+  for (int j = warp_global / per; j < n_jobs; j += lanes_of_jobs) {
+    const int g = E.rr_jobs[j];
+    const int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
+    const int buf = ti[TI_BUF], count = ti[TI_NODES];
+    TreeView To = tree_view(E, g, buf ^ 1);
+    TreeView Tn = tree_view(E, g, buf);
+    const int16_t* remap = E.remap + (size_t)g * E.d.cap;
+    for (int i = 1 + r; i < count; i += per) commit_copy_node(To, Tn, (size_t)remap[i], i, E.d.Ap, E.d.ncp);
+  }
+}
+
+AZ_DEV int game_commit(const AzState& E, int g, int move, double* best_child_q, bool defer = false) {
   const AzDims& d = E.d;
   const int Ap = d.Ap;
   int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
@@ -706,58 +812,18 @@ AZ_DEV int game_commit(const AzState& E, int g, int move, double* best_child_q) 
       w_sync();
     }
     W_LANE0 { Tn.parent[0] = -1; Tn.pmove[0] = -1; }
-    // ---- pass 2, payload: statistics rows, cached position and flags of every kept node.  No node depends on another one here;
-    //      all loads of a node are issued before its first store and the rows of a later node are prefetched meanwhile.
-    const bool cache = To.nboard != nullptr;
-    for (int i = 0; i < count; ++i) {
-      const size_t old = (size_t)remap[i];
-      if (i + 4 < count) {
-        const size_t pf = (size_t)remap[i + 4];
-        w_prefetch(To.N + pf * Ap, Ap * 4);
-        w_prefetch(To.W + pf * Ap, Ap * 4);
-        w_prefetch(To.P + pf * Ap, Ap * 4);
-        if (cache) { w_prefetch(To.nboard + pf * d.ncp, d.ncp); w_prefetch(To.nlegal + pf * Ap, Ap); }
-      }
-      const uint8_t ex = To.expanded[old];
-      const int8_t tp = To.to_play[old];
-      const int16_t ko = cache ? To.nko[old] : (int16_t)-1;
-      for (int a00 = 0; a00 < Ap; a00 += KC * AZ_WIDTH) {
-        float fn[KC], fw[KC], fp[KC];
-        uint8_t lg[KC];
-        int8_t bd[KC];
-#pragma unroll
-        for (int k = 0; k < KC; ++k) {
-          const int a = a00 + k * AZ_WIDTH + AZ_LANE;
-          fn[k] = fw[k] = fp[k] = 0.f; lg[k] = 0; bd[k] = 0;
-          if (a < Ap) {
-            fn[k] = To.N[old * Ap + a];
-            fw[k] = To.W[old * Ap + a];
-            fp[k] = To.P[old * Ap + a];
-            if (cache) {
-              lg[k] = To.nlegal[old * Ap + a];
-              if (a < d.ncp) bd[k] = To.nboard[old * d.ncp + a];
-            }
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < KC; ++k) {
-          const int a = a00 + k * AZ_WIDTH + AZ_LANE;
-          if (a < Ap) {
-            Tn.N[(size_t)i * Ap + a] = fn[k];
-            Tn.W[(size_t)i * Ap + a] = fw[k];
-            Tn.P[(size_t)i * Ap + a] = fp[k];
-            if (cache) {
-              Tn.nlegal[(size_t)i * Ap + a] = lg[k];
-              if (a < d.ncp) Tn.nboard[(size_t)i * d.ncp + a] = bd[k];
-            }
-          }
-        }
-      }
+    // ---- pass 2, payload: statistics rows, cached position and flags of every kept node.  No node depends on another one here.
+    //      With `defer` only the new root is copied by this warp (search_enter needs its rows right away); nodes 1.. are left to
+    //      k_reroot_payload, which spreads them over the whole grid (az_engine.cu launches it right behind k_advance).
+    const int n_inline = defer ? 1 : count;
+    for (int i = 0; i < n_inline; ++i) {
+      if (i + 4 < n_inline) commit_prefetch_node(To, (size_t)remap[i + 4], Ap, d.ncp);
+      commit_copy_node(To, Tn, (size_t)remap[i], i, Ap, d.ncp);
+    }
+    if (defer && count > 1) {
       W_LANE0 {
-        Tn.expanded[i] = ex;
-        Tn.to_play[i] = tp;
-        Tn.vloss[i] = 0;
-        if (cache) Tn.nko[i] = ko;
+        const int j = atomic_add_i(E.rr_count, 1);
+        E.rr_jobs[j] = g;
       }
     }
     w_sync();
@@ -806,7 +872,7 @@ AZ_DEV void game_new(const AzState& E, int g, Sim& S) {
   w_sync();
 }
 
-AZ_DEV void game_advance(const AzState& E, int g, Sim& S) {
+AZ_DEV void game_advance(const AzState& E, int g, Sim& S, bool defer_payload = false) {
   const AzDims& d = E.d;
   int32_t* ti = E.tree_i + (size_t)g * TREE_INTS;
   if (!ti[TI_ACTIVE] || ti[TI_STATE] != ST_DONE) return;
@@ -869,7 +935,7 @@ AZ_DEV void game_advance(const AzState& E, int g, Sim& S) {
     W_LANE0 ti[TI_WARM] = (ei[EI_STEPS] <= E.s.warm_up_steps) ? 1 : 0;
     w_sync();
     // evaluation matches search every move from a fresh root (`root_node=None`, pipeline.py:834-840): the tree is dropped
-    const int kept = E.s.match ? 0 : game_commit(E, g, play, nullptr);
+    const int kept = E.s.match ? 0 : game_commit(E, g, play, nullptr, defer_payload);
     if (kept) {
       W_LANE0 ti[TI_STATE] = ST_SEARCH_INIT;
       w_sync();

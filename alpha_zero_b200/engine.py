@@ -24,6 +24,22 @@ def state_dict_tensors(state_dict):
     return out
 
 
+class _PinnedBlock:
+    """cudaHostAlloc'ed bytes exposed through the array interface: numpy arrays made from it keep it alive."""
+
+    def __init__(self, binding, nbytes):
+        p = C.c_void_p()
+        binding.check(binding.dll.az_host_alloc(C.c_size_t(nbytes), C.byref(p)))
+        self._free, self._ptr = binding.dll.az_host_free, p
+        self.__array_interface__ = {'data': (p.value, False), 'shape': (nbytes,), 'typestr': '|u1', 'version': 3}
+
+    def __del__(self):
+        try:
+            self._free(self._ptr)
+        except Exception:
+            pass
+
+
 class Engine:
     def __init__(self, game, board_size, num_games=1, max_simulations=800, max_parallel=8, komi=7.5, max_steps=0, num_to_win=5,
                  num_stack=8, net=None, precision='fp32', device=0, seed=1, sample_ring=0, binding=None):
@@ -44,16 +60,13 @@ class Engine:
         self.planes = 2 * num_stack + 1
         self.max_parallel = max_parallel
         self._active = None
-        self._host_blocks, self._drain_buf = [], None
+        self._drain_buf = None
 
     def close(self):
         if getattr(self, 'h', None):
             self.b.dll.az_destroy(self.h)
             self.h = None
-            self._drain_buf = None
-            for p in self._host_blocks:
-                self.b.dll.az_host_free(p)
-            self._host_blocks = []
+            self._drain_buf = None  # the pinned blocks go when the last array the caller still holds goes
 
     def __del__(self):
         try:
@@ -267,19 +280,17 @@ class Engine:
         self.b.check(self.b.dll.az_get_counters(self.h, C.byref(c)))
         return {k: int(getattr(c, k)) for k, _ in AzCounters._fields_}
 
-    def _pinned(self, nbytes):
-        """Page-locked host block owned by this engine (freed in close())."""
-        p = C.c_void_p()
-        self.b.check(self.b.dll.az_host_alloc(C.c_size_t(nbytes), C.byref(p)))
-        self._host_blocks.append(p)
-        return (C.c_char * nbytes).from_address(p.value)
+    def _pinned(self, nbytes, dtype):
+        """numpy view of a page-locked host block; the block is released when the last view of it is garbage-collected, so arrays
+        handed to the caller stay valid after close()."""
+        return np.asarray(_PinnedBlock(self.b, nbytes)).view(dtype)
 
     def _drain_buffers(self, max_samples):
         if self._drain_buf is None or self._drain_buf[0] < max_samples:
-            st = np.frombuffer(self._pinned(max_samples * self.obs_bytes), dtype=np.int8).reshape(max_samples, self.obs_bytes)
-            pis = np.frombuffer(self._pinned(max_samples * self.A * 4), dtype=np.float32).reshape(max_samples, self.A)
-            z = np.frombuffer(self._pinned(max_samples * 4), dtype=np.float32)
-            mv = np.frombuffer(self._pinned(max_samples * 2), dtype=np.int16)
+            st = self._pinned(max_samples * self.obs_bytes, np.int8).reshape(max_samples, self.obs_bytes)
+            pis = self._pinned(max_samples * self.A * 4, np.float32).reshape(max_samples, self.A)
+            z = self._pinned(max_samples * 4, np.float32)
+            mv = self._pinned(max_samples * 2, np.int16)
             self._drain_buf = (max_samples, st, pis, z, mv)
         return self._drain_buf[1:]
 
