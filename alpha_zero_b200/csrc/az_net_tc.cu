@@ -876,6 +876,7 @@ k_conv_tc_x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       }
       mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
       tc_fence_after();
+      bool arrived = false;
 #pragma unroll 1
       for (int ps = 0; ps < 2 * npass_c; ++ps) {
         const int h = ps >= npass_c ? 1 : 0, pc = ps - h * npass_c;
@@ -937,6 +938,17 @@ k_conv_tc_x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         unsigned char* myrow = stage + (size_t)lane * srow;
         {
           tc_wait_ld();
+          if (ps == 2 * npass_c - 1) {
+            // the accumulator stage is free as soon as its last TMEM read has landed in registers: hand it back to the MMA warps
+            // BEFORE this pass's arithmetic and global stores (the release of a remote arrive otherwise waits for those stores)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (PAIR && crank != 0) mbar_arrive_remote(&tempty_bar[acc], 0);
+              else mbar_arrive(&tempty_bar[acc]);
+            }
+            arrived = true;
+          }
           __align__(16) __nv_bfloat16 o[32];
           if (valid) {
             __align__(16) __nv_bfloat16 rr[32];
@@ -944,12 +956,19 @@ k_conv_tc_x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
               for (int k = 0; k < 4; ++k) reinterpret_cast<uint4*>(rr)[k] = *reinterpret_cast<const uint4*>(myrow + k * 16);
             }
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias + cc);  // 16-byte aligned: s_bias follows 16-byte multiples, cc % 32 == 0
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float f = __uint_as_float(v[j]) + s_bias[cc + j];
-              if (L.has_res) f += __bfloat162float(rr[j]);
-              if (L.relu) f = fmaxf(f, 0.f);
-              o[j] = __float2bfloat16(f);
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bq = b4[j4];
+              const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int j = j4 * 4 + jj;
+                float f = __uint_as_float(v[j]) + bb[jj];
+                if (L.has_res) f += __bfloat162float(rr[j]);
+                if (L.relu) f = fmaxf(f, 0.f);
+                o[j] = __float2bfloat16(f);
+              }
             }
           } else {
 #pragma unroll
@@ -969,11 +988,13 @@ k_conv_tc_x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
         __syncwarp();
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (PAIR && crank != 0) mbar_arrive_remote(&tempty_bar[acc], 0);
-        else mbar_arrive(&tempty_bar[acc]);
+      if (!arrived) {  // split path: every pass ends with its own tcgen05.wait::ld
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR && crank != 0) mbar_arrive_remote(&tempty_bar[acc], 0);
+          else mbar_arrive(&tempty_bar[acc]);
+        }
       }
     }
   }

@@ -64,8 +64,15 @@ AZ_DEV void tree_init_node(const AzState& E, TreeView& T, int idx, int parent, i
     T.to_play[idx] = (int8_t)to_play;
     T.expanded[idx] = 0;
     T.vloss[idx] = 0;
+    if (T.nko) T.nko[idx] = -1;  // neither a ko point nor a cached terminal result yet
   }
 }
+
+// A terminal child is never expanded and every later visit re-steps the environment to find the same result again
+// (mcts_v2.py:604-608).  With the node cache the result is kept in the node's ko field instead (a terminal node has no ko point
+// to remember): AZ_TERM_BASE + 2 * reward of the mover.  Late positions hit terminals on most of their 2 * P tries, and the
+// select kernel ends with its slowest warp.
+#define AZ_TERM_BASE 30000
 
 // Lazy child creation at selection time (mcts_v2.py:182-183).  `n_nodes` is the caller's register copy of the pool size.
 AZ_DEV int tree_new_node(const AzState& E, TreeView& T, int parent, int move, int to_play, int& n_nodes, LocalCounters& lc) {
@@ -571,6 +578,17 @@ AZ_DEV void game_collect_nc(const AzState& E, int g, Sim& S, LocalCounters& lc) 
         }
         if (aborted) break;
         w_sync();
+        {
+          const int tk = T.nko[node];
+          if (tk >= AZ_TERM_BASE - 2) {  // a terminal found by an earlier descent: same backup, no board work
+            lc.descents++;
+            lc.depth += depth;
+            const float v = -(0.5f * (float)(tk - AZ_TERM_BASE));
+            if (depth <= AZ_PATH) path_backup(E, T, g, S.path_k, depth, v, lc);
+            else tree_backup(E, T, g, node, v, lc);
+            continue;
+          }
+        }
         // ---- the position of `parent`, then the one ply that leads to the leaf
         if (parent == 0) {
           sim_load(E, g, S);
@@ -604,6 +622,7 @@ AZ_DEV void game_collect_nc(const AzState& E, int g, Sim& S, LocalCounters& lc) 
         lc.depth += depth;
         if (o.done) {  // terminal: never expanded, back up the game result (mcts_v2.py:604-608)
           const float v = -(0.5f * (float)o.reward_x2);
+          W_LANE0 T.nko[node] = (int16_t)(AZ_TERM_BASE + o.reward_x2);
           if (depth <= AZ_PATH) path_backup(E, T, g, S.path_k, depth, v, lc);
           else tree_backup(E, T, g, node, v, lc);
           continue;

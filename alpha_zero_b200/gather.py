@@ -25,16 +25,25 @@ def shard_slots(total_games, rank, world):
 class GatheredSamples:
     """Every rank's samples of one round, rank-major, on the gathering device."""
 
-    def __init__(self, states, pis, zs, counts, shape):
-        self.states, self.pis, self.zs, self.counts, self._shape = states, pis, zs, counts, shape
+    def __init__(self, states, pis, zs, counts, shape, pinned=None):
+        self.states, self.pis, self.zs, self.counts, self._shape, self._pinned = states, pis, zs, counts, shape, pinned
 
     def __len__(self):
         return int(self.zs.shape[0])
 
     def to_host(self):
-        """numpy copies (states int8 [n, planes, N, N], pis f32 [n, A], z f32 [n]): one device->host copy per array."""
+        """numpy arrays (states int8 [n, planes, N, N], pis f32 [n, A], z f32 [n]).  On a CUDA device the three copies go
+        asynchronously into the gatherer's page-locked buffers (one synchronisation; the arrays are views that the next
+        to_host() overwrites — copy what must outlive the round); on the CPU (gloo tests) they are plain copies."""
         n = len(self)
-        return (self.states.cpu().numpy().reshape((n,) + self._shape), self.pis.cpu().numpy(), self.zs.cpu().numpy())
+        if self._pinned is None or not self.states.is_cuda:
+            return (self.states.cpu().numpy().reshape((n,) + self._shape), self.pis.cpu().numpy(), self.zs.cpu().numpy())
+        hs, hp, hz = self._pinned(n)
+        hs[:n].copy_(self.states, non_blocking=True)
+        hp[:n].copy_(self.pis, non_blocking=True)
+        hz[:n].copy_(self.zs, non_blocking=True)
+        torch.cuda.current_stream(self.states.device).synchronize()
+        return (hs[:n].numpy().reshape((n,) + self._shape), hp[:n].numpy(), hz[:n].numpy())
 
 
 class DeviceSampleGatherer:
@@ -60,12 +69,22 @@ class DeviceSampleGatherer:
             self.cnts = torch.zeros((self.world,), dtype=torch.int64, **kw)
         self.total = 0
         self.bytes_sent = 0
+        self._host = None
+
+    def _pinned(self, n):
+        """Page-locked host staging for to_host(), grown on demand (only the rank that reads the samples ever allocates it)."""
+        if self._host is None or self._host[0].shape[0] < n:
+            rows = max(n, self.capacity)
+            self._host = (torch.empty((rows, self.sdim), dtype=torch.int8, pin_memory=True),
+                          torch.empty((rows, self.adim), dtype=torch.float32, pin_memory=True),
+                          torch.empty((rows,), dtype=torch.float32, pin_memory=True))
+        return self._host
 
     def push(self):
         """Pack this rank's finished games and exchange.  Returns (records of THIS rank's games, GatheredSamples of all ranks)."""
         games, n = self.engine.gather_pack(self.blk_s.data_ptr(), self.blk_p.data_ptr(), self.blk_z.data_ptr(), self.capacity)
         if self.world == 1:
-            out = GatheredSamples(self.blk_s[:n], self.blk_p[:n], self.blk_z[:n], [n], self.shape)
+            out = GatheredSamples(self.blk_s[:n], self.blk_p[:n], self.blk_z[:n], [n], self.shape, self._pinned)
             self.total += n
             return games, out
         self.cnt[0] = n
@@ -73,7 +92,7 @@ class DeviceSampleGatherer:
         counts = [int(c) for c in self.cnts.tolist()]  # world integers: the only host read of the exchange
         m = max(counts)
         if m == 0:
-            return games, GatheredSamples(self.blk_s[:0], self.blk_p[:0], self.blk_z[:0], counts, self.shape)
+            return games, GatheredSamples(self.blk_s[:0], self.blk_p[:0], self.blk_z[:0], counts, self.shape, self._pinned)
         w = self.world
         dist.all_gather_into_tensor(self.out_s[: w * m], self.blk_s[:m], group=self.group)
         dist.all_gather_into_tensor(self.out_p[: w * m], self.blk_p[:m], group=self.group)
@@ -86,4 +105,4 @@ class DeviceSampleGatherer:
             P = torch.cat([self.out_p[r * m: r * m + c] for r, c in enumerate(counts)])
             Z = torch.cat([self.out_z[r * m: r * m + c] for r, c in enumerate(counts)])
         self.total += sum(counts)
-        return games, GatheredSamples(S, P, Z, counts, self.shape)
+        return games, GatheredSamples(S, P, Z, counts, self.shape, self._pinned)
