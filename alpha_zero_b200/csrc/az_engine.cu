@@ -1258,10 +1258,8 @@ extern "C" int az_last_net_ms(az_engine* e, float* ms, int32_t* n_evals) {
   AZ_ENTER(e);
   if (!e || !ms) return az_fail(AZ_ERR_BAD_ARG, "null argument");
 #ifndef AZ_EMU
-  cudaEventSynchronize(e->ev1);
-  float t = 0.f;
-  if (cudaEventElapsedTime(&t, e->ev0, e->ev1) != cudaSuccess) t = 0.f;
-  *ms = t;
+  // the conv launches of the most recent network call alone (events recorded inside the forward, around the tower)
+  *ms = e->net ? aznet_last_tower_ms(e->net) : 0.f;
   int32_t tot[2] = {0, 0};
   rt_d2h(e->rt, tot, e->E.leaf_total + (e->pipeline ? 4 : 0), sizeof(tot));  // pipeline: the events bracket the second half's tower
   if (n_evals) *n_evals = tot[0];

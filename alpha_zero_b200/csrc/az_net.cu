@@ -145,6 +145,8 @@ AzNet* aznet_create(const AzDims& d, const az_config& cfg, AzRt& rt, int max_lea
   n->act_x = rt_alloc(n->rows_total * cw * esz);
   n->act_mid = rt_alloc(n->rows_total * cw * esz);
   n->dbg_count = (int32_t*)rt_alloc(sizeof(int32_t));
+  cudaEventCreate(&n->ev_tower[0]);
+  cudaEventCreate(&n->ev_tower[1]);
   if (!n->act_in || !n->act_x || !n->act_mid || !n->dbg_count) {
     err = "activation buffers: out of device memory (" + std::to_string((n->rows_total * (g.cin_pad + 2 * cw) * esz) >> 20) + " MB)";
     aznet_destroy(n);
@@ -167,11 +169,19 @@ void aznet_destroy(AzNet* n) {
   rt_free(n->act_x);
   rt_free(n->act_mid);
   rt_free(n->dbg_count);
+  for (int k = 0; k < 2; ++k)
+    if (n->ev_tower[k]) cudaEventDestroy(n->ev_tower[k]);
   for (void* p : n->allocs) rt_free(p);
   delete n;
 }
 
 double aznet_flops_per_eval(const AzNet* n) { return n ? n->flops : 0.0; }
+float aznet_last_tower_ms(const AzNet* n) {
+  float ms = 0.f;
+  if (!n || !n->ev_tower[1] || cudaEventSynchronize(n->ev_tower[1]) != cudaSuccess) return 0.f;
+  if (cudaEventElapsedTime(&ms, n->ev_tower[0], n->ev_tower[1]) != cudaSuccess) { cudaGetLastError(); return 0.f; }
+  return ms;
+}
 int aznet_padded_filters(const AzNet* n) { return n ? n->C : 0; }
 int aznet_tc_mode_of(const AzNet* n) { return n && aznet_is_tc(n) ? aznet_tc_mode(n) : -1; }
 int aznet_ready(const AzNet* n) { return n && n->ready; }
@@ -347,6 +357,7 @@ int aznet_forward(AzNet* n, AzRt& rt, const int8_t* obs_base, const int32_t* row
   dim3 grid((unsigned)((Mmax + 63) / 64), (unsigned)((n->C + 63) / 64));
   float* X = (float*)n->act_x;
   float* MID = (float*)n->act_mid;
+  cudaEventRecord(n->ev_tower[0], rt.stream);
   k_conv_f32<<<grid, 256, 0, rt.stream>>>((const float*)n->act_in, n->conv_w[0], n->conv_b[0], nullptr, X, n_rows_dev, g, g.cin_pad, n->C, 1);
   rt.launches++;
   for (int b = 0; b < n->blocks; ++b) {
@@ -354,6 +365,7 @@ int aznet_forward(AzNet* n, AzRt& rt, const int8_t* obs_base, const int32_t* row
     k_conv_f32<<<grid, 256, 0, rt.stream>>>(MID, n->conv_w[2 + 2 * b], n->conv_b[2 + 2 * b], X, X, n_rows_dev, g, n->C, n->C, 1);
     rt.launches += 2;
   }
+  cudaEventRecord(n->ev_tower[1], rt.stream);
   launch_heads<float>(rt.stream, X, row_list, n_rows_dev, n->hp, g, n->C, n->C, 0, n->A, n->fc, priors_base, values_base, pri_stride, max_rows);
   rt.launches++;
   cudaError_t e = cudaGetLastError();

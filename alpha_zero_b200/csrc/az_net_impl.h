@@ -43,6 +43,8 @@ struct AzNet {
   std::vector<void*> allocs;
   double flops = 0.0;
   AzNetTc* tc = nullptr;
+  // CUDA events around the conv launches of the most recent forward (the tower alone: no input / heads kernels), for the roofline
+  cudaEvent_t ev_tower[2] = {nullptr, nullptr};
 };
 
 int aznet_tc_create(AzNet* n, AzRt& rt, std::string& err);
