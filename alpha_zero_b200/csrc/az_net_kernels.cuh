@@ -64,18 +64,26 @@ static __global__ void __launch_bounds__(256) k_heads(const T* __restrict__ feat
     float p0 = 0.f, p1 = 0.f, v0 = 0.f;
     if (sizeof(T) == 2) {
       const uint4* f4 = reinterpret_cast<const uint4*>(f);
-      const int nchunk = (split ? 2 * C : C) / 8;
-      for (int c8 = 0; c8 < nchunk; ++c8) {
-        const uint4 raw = f4[c8];
-        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-        const int cb = c8 * 8 >= C ? c8 * 8 - C : c8 * 8;
+      const int nchunk = (split ? 2 * C : C) / 8;  // a multiple of 8 (C is a multiple of 64)
+      for (int c80 = 0; c80 < nchunk; c80 += 4) {
+        // four 16-byte loads of the row in flight before the first is consumed (rows of neighbouring threads are 256+ bytes apart:
+        // the loop is latency bound, not bandwidth bound)
+        uint4 raw4[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float a0 = __uint_as_float(w[k] << 16), a1 = __uint_as_float(w[k] & 0xffff0000u);
-          const int c = cb + k * 2;
-          p0 = fmaf(a0, s_w[c], fmaf(a1, s_w[c + 1], p0));
-          p1 = fmaf(a0, s_w[C + c], fmaf(a1, s_w[C + c + 1], p1));
-          v0 = fmaf(a0, s_w[2 * C + c], fmaf(a1, s_w[2 * C + c + 1], v0));
+        for (int u = 0; u < 4; ++u) raw4[u] = f4[c80 + u];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c8 = c80 + u;
+          const uint32_t w[4] = {raw4[u].x, raw4[u].y, raw4[u].z, raw4[u].w};
+          const int cb = c8 * 8 >= C ? c8 * 8 - C : c8 * 8;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float a0 = __uint_as_float(w[k] << 16), a1 = __uint_as_float(w[k] & 0xffff0000u);
+            const int c = cb + k * 2;
+            p0 = fmaf(a0, s_w[c], fmaf(a1, s_w[c + 1], p0));
+            p1 = fmaf(a0, s_w[C + c], fmaf(a1, s_w[C + c + 1], p1));
+            v0 = fmaf(a0, s_w[2 * C + c], fmaf(a1, s_w[2 * C + c + 1], v0));
+          }
         }
       }
     } else {

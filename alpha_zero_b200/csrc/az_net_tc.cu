@@ -664,6 +664,7 @@ struct XLayer {
   int sub_stride;  // the same rounded up to 1024 (swizzle atom alignment of the next slot)
   int bstages;     // weight ring depth: X_BSTAGES for a pair (half chunks), half of it for a single CTA (same bytes)
   int ostride;     // elements per activation row of `out` / `res`: cout, or 3 * cout for the split-bf16 rows [hi | lo | hi]
+  int ksteps;      // K = 16 steps per 64-channel chunk that carry data: 4, or 2 for the input layer (17 planes in channels 0..31)
 };
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
@@ -808,11 +809,13 @@ k_conv_tc_x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
               const uint32_t blo = b_lo[bstage];
 #pragma unroll
               for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
-                const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(alo + (uint32_t)k4 * 2u);
-                const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(blo + (uint32_t)k4 * 2u);
-                const uint32_t accum = (kk | dxi | dyi | k4) != 0 ? 1u : 0u;
-                if (PAIR) tc_mma_pair(d_tmem, ad, bd, idesc, accum);
-                else tc_mma(d_tmem, ad, bd, idesc, accum);
+                if (k4 < L.ksteps) {  // uniform: the input layer's channels 32..63 are zero, its chunk needs two steps only
+                  const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(alo + (uint32_t)k4 * 2u);
+                  const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(blo + (uint32_t)k4 * 2u);
+                  const uint32_t accum = (kk | dxi | dyi | k4) != 0 ? 1u : 0u;
+                  if (PAIR) tc_mma_pair(d_tmem, ad, bd, idesc, accum);
+                  else tc_mma(d_tmem, ad, bd, idesc, accum);
+                }
               }
               if (PAIR) tc_commit_pair(&b_empty[bstage]);
               else tc_commit(&b_empty[bstage]);
@@ -1228,6 +1231,7 @@ int aznet_tc_layer(AzNet* n, AzRt& rt, int li, bool with_res, const int32_t* n_r
     X5.Hc = g.Hc; X5.RP = g.RP; X5.guard = g.guard; X5.TH = tc->x_TH; X5.sub_bytes = tc->x_sub_bytes; X5.sub_stride = tc->x_sub_stride;
     X5.bstages = pair ? X_BSTAGES : X_BSTAGES / 2;
     X5.cin = cin; X5.cout = n->C; X5.relu = 1; X5.has_res = resp ? 1 : 0; X5.ostride = tc->split ? 3 * n->C : n->C;
+    X5.ksteps = (li == 0 && !tc->split && g.planes <= 32) ? 2 : 4;
     const CUtensorMap& ma = src == 0 ? tc->xmap_in : (src == 1 ? tc->xmap_x : tc->xmap_mid);
     if (!pair) {
       if (tc->split) k_conv_tc_x<false, true><<<xgrid, H_THREADS, tc->x_smem, rt.stream>>>(ma, tc->map_w[li], bias, resp, outp, n_rows_dev, X5);
