@@ -31,8 +31,10 @@ def transformations(binding, tag):
     eng.close()
 
 
-def uniform_replay_semantics(binding):
-    """Circular overwrite, counters and seeded sampling behave like core/replay.py:35-116 (checked against a plain-Python model)."""
+def uniform_replay_semantics(binding, make_out=None):
+    """Circular overwrite, counters and seeded sampling behave like core/replay.py:35-116 (checked against a plain-Python model).
+    `make_out(batch, obs_bytes, A)` -> ((states_ptr, pis_ptr, values_ptr), read) supplies caller-owned "device" buffers for the
+    zero-copy path: DeviceReplay.sample(out=...) must say True (None stays reserved for "not enough samples yet")."""
     eng = Engine('go', 9, num_games=1, max_simulations=8, max_parallel=1, binding=binding)
     rp = DeviceReplay(eng, capacity=10, random_state=np.random.RandomState(4))
     model = [None] * 10
@@ -55,6 +57,15 @@ def uniform_replay_semantics(binding):
         np.testing.assert_array_equal(batch.state, np.stack([model[i].state for i in idx]))
         np.testing.assert_array_equal(batch.pi_prob, np.stack([model[i].pi_prob for i in idx]))
         np.testing.assert_array_equal(batch.value, np.array([model[i].value for i in idx], dtype=np.float32))
+    if make_out is not None:
+        ptrs, read = make_out(6, 17 * 81, 82)
+        assert rp.sample(6, out=ptrs) is True
+        idx = ref_rng.randint(low=0, high=10, size=6)
+        st, pi, z = read()
+        np.testing.assert_array_equal(st.reshape(6, 17, 9, 9), np.stack([model[i].state for i in idx]))
+        np.testing.assert_array_equal(pi, np.stack([model[i].pi_prob for i in idx]))
+        np.testing.assert_array_equal(z, np.array([model[i].value for i in idx], dtype=np.float32))
+        assert DeviceReplay(Engine('go', 9, num_games=1, max_simulations=8, max_parallel=1, binding=binding), 4, np.random.RandomState(1)).sample(2, out=ptrs) is None
     # augmentation consumes python's `random` exactly like apply_random_transformation
     random.seed(9)
     expect = []

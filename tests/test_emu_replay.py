@@ -25,7 +25,13 @@ def test_transformations_match_reference(emu, tag):
 
 
 def test_uniform_replay_semantics(emu):
-    replaycheck.uniform_replay_semantics(emu)
+    def make_out(batch, obs_bytes, A):  # the emulation's "device" memory is host memory
+        import numpy as np
+
+        st, pi, z = np.zeros((batch, obs_bytes), np.int8), np.zeros((batch, A), np.float32), np.zeros(batch, np.float32)
+        return (st.ctypes.data, pi.ctypes.data, z.ctypes.data), lambda: (st, pi, z)
+
+    replaycheck.uniform_replay_semantics(emu, make_out)
 
 
 def test_ingest_equals_drain(emu):

@@ -22,7 +22,13 @@ def test_transformations_match_reference(cuda, tag):
 
 
 def test_uniform_replay_semantics(cuda):
-    replaycheck.uniform_replay_semantics(cuda)
+    def make_out(batch, obs_bytes, A):
+        st = torch.zeros((batch, obs_bytes), dtype=torch.int8, device='cuda')
+        pi = torch.zeros((batch, A), dtype=torch.float32, device='cuda')
+        z = torch.zeros((batch,), dtype=torch.float32, device='cuda')
+        return (st.data_ptr(), pi.data_ptr(), z.data_ptr()), lambda: (st.cpu().numpy(), pi.cpu().numpy(), z.cpu().numpy())
+
+    replaycheck.uniform_replay_semantics(cuda, make_out)
 
 
 def test_ingest_equals_drain(cuda):
