@@ -1258,8 +1258,9 @@ extern "C" int az_last_net_ms(az_engine* e, float* ms, int32_t* n_evals) {
   AZ_ENTER(e);
   if (!e || !ms) return az_fail(AZ_ERR_BAD_ARG, "null argument");
 #ifndef AZ_EMU
-  // the conv launches of the most recent network call alone (events recorded inside the forward, around the tower)
-  *ms = e->net ? aznet_last_tower_ms(e->net) : 0.f;
+  // the conv launches alone (events recorded inside the forward, around the tower), mean over the last (up to 64) network calls
+  int averaged = 0;
+  *ms = e->net ? aznet_last_tower_ms(e->net, &averaged) : 0.f;
   int32_t tot[2] = {0, 0};
   rt_d2h(e->rt, tot, e->E.leaf_total + (e->pipeline ? 4 : 0), sizeof(tot));  // pipeline: the events bracket the second half's tower
   if (n_evals) *n_evals = tot[0];

@@ -17,6 +17,8 @@
 //   AZ_NET_BF16  az_net_tc.cu: tcgen05.mma (bf16 x bf16 -> f32 in TMEM), TMA-staged operands.
 #include <math.h>
 
+#include <algorithm>
+
 #include <thread>
 #include <vector>
 
@@ -145,8 +147,7 @@ AzNet* aznet_create(const AzDims& d, const az_config& cfg, AzRt& rt, int max_lea
   n->act_x = rt_alloc(n->rows_total * cw * esz);
   n->act_mid = rt_alloc(n->rows_total * cw * esz);
   n->dbg_count = (int32_t*)rt_alloc(sizeof(int32_t));
-  cudaEventCreate(&n->ev_tower[0]);
-  cudaEventCreate(&n->ev_tower[1]);
+  for (int k = 0; k < AzNet::kTowerRing; ++k) { cudaEventCreate(&n->ev_tower[k][0]); cudaEventCreate(&n->ev_tower[k][1]); }
   if (!n->act_in || !n->act_x || !n->act_mid || !n->dbg_count) {
     err = "activation buffers: out of device memory (" + std::to_string((n->rows_total * (g.cin_pad + 2 * cw) * esz) >> 20) + " MB)";
     aznet_destroy(n);
@@ -169,18 +170,30 @@ void aznet_destroy(AzNet* n) {
   rt_free(n->act_x);
   rt_free(n->act_mid);
   rt_free(n->dbg_count);
-  for (int k = 0; k < 2; ++k)
-    if (n->ev_tower[k]) cudaEventDestroy(n->ev_tower[k]);
+  for (int k = 0; k < AzNet::kTowerRing; ++k)
+    for (int j = 0; j < 2; ++j)
+      if (n->ev_tower[k][j]) cudaEventDestroy(n->ev_tower[k][j]);
   for (void* p : n->allocs) rt_free(p);
   delete n;
 }
 
 double aznet_flops_per_eval(const AzNet* n) { return n ? n->flops : 0.0; }
-float aznet_last_tower_ms(const AzNet* n) {
-  float ms = 0.f;
-  if (!n || !n->ev_tower[1] || cudaEventSynchronize(n->ev_tower[1]) != cudaSuccess) return 0.f;
-  if (cudaEventElapsedTime(&ms, n->ev_tower[0], n->ev_tower[1]) != cudaSuccess) { cudaGetLastError(); return 0.f; }
-  return ms;
+float aznet_last_tower_ms(const AzNet* n, int* n_averaged) {
+  if (n_averaged) *n_averaged = 0;
+  if (!n || !n->n_forwards) return 0.f;
+  const unsigned long long last = n->n_forwards - 1;
+  if (cudaEventSynchronize(n->ev_tower[last % AzNet::kTowerRing][1]) != cudaSuccess) { cudaGetLastError(); return 0.f; }
+  const int cnt = (int)std::min<unsigned long long>(n->n_forwards, (unsigned long long)AzNet::kTowerRing);
+  double sum = 0.0;
+  int used = 0;
+  for (int k = 0; k < cnt; ++k) {
+    cudaEvent_t* ev = const_cast<cudaEvent_t*>(n->ev_tower[(last - k) % AzNet::kTowerRing]);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) { sum += ms; used++; }
+    else cudaGetLastError();
+  }
+  if (n_averaged) *n_averaged = used;
+  return used ? (float)(sum / used) : 0.f;
 }
 int aznet_padded_filters(const AzNet* n) { return n ? n->C : 0; }
 int aznet_tc_mode_of(const AzNet* n) { return n && aznet_is_tc(n) ? aznet_tc_mode(n) : -1; }
@@ -357,7 +370,8 @@ int aznet_forward(AzNet* n, AzRt& rt, const int8_t* obs_base, const int32_t* row
   dim3 grid((unsigned)((Mmax + 63) / 64), (unsigned)((n->C + 63) / 64));
   float* X = (float*)n->act_x;
   float* MID = (float*)n->act_mid;
-  cudaEventRecord(n->ev_tower[0], rt.stream);
+  cudaEvent_t* evp = n->ev_tower[n->n_forwards % AzNet::kTowerRing];
+  cudaEventRecord(evp[0], rt.stream);
   k_conv_f32<<<grid, 256, 0, rt.stream>>>((const float*)n->act_in, n->conv_w[0], n->conv_b[0], nullptr, X, n_rows_dev, g, g.cin_pad, n->C, 1);
   rt.launches++;
   for (int b = 0; b < n->blocks; ++b) {
@@ -365,7 +379,8 @@ int aznet_forward(AzNet* n, AzRt& rt, const int8_t* obs_base, const int32_t* row
     k_conv_f32<<<grid, 256, 0, rt.stream>>>(MID, n->conv_w[2 + 2 * b], n->conv_b[2 + 2 * b], X, X, n_rows_dev, g, n->C, n->C, 1);
     rt.launches += 2;
   }
-  cudaEventRecord(n->ev_tower[1], rt.stream);
+  cudaEventRecord(evp[1], rt.stream);
+  n->n_forwards++;
   launch_heads<float>(rt.stream, X, row_list, n_rows_dev, n->hp, g, n->C, n->C, 0, n->A, n->fc, priors_base, values_base, pri_stride, max_rows);
   rt.launches++;
   cudaError_t e = cudaGetLastError();

@@ -25,5 +25,6 @@ int aznet_debug_layer(AzNet* n, AzRt& rt, int li, const float* in, const float* 
 int aznet_tc_mode_of(const AzNet* n);
 int aznet_padded_filters(const AzNet* n);
 double aznet_flops_per_eval(const AzNet* n);
-float aznet_last_tower_ms(const AzNet* n);  // conv launches of the most recent forward, CUDA events on the engine stream
+// mean device time of the conv launches of a forward over the most recent (up to 64) forwards, CUDA events on the engine stream
+float aznet_last_tower_ms(const AzNet* n, int* n_averaged);
 int aznet_ready(const AzNet* n);

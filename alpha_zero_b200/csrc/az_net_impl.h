@@ -44,7 +44,10 @@ struct AzNet {
   double flops = 0.0;
   AzNetTc* tc = nullptr;
   // CUDA events around the conv launches of the most recent forward (the tower alone: no input / heads kernels), for the roofline
-  cudaEvent_t ev_tower[2] = {nullptr, nullptr};
+  // (a ring of the last AZ_TOWER_RING forwards: az_last_net_ms reports their mean, one tick alone is a noisy sample)
+  static constexpr int kTowerRing = 64;
+  cudaEvent_t ev_tower[kTowerRing][2] = {};
+  unsigned long long n_forwards = 0;
 };
 
 int aznet_tc_create(AzNet* n, AzRt& rt, std::string& err);

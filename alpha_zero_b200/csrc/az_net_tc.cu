@@ -1294,9 +1294,11 @@ int aznet_tc_forward(AzNet* n, AzRt& rt, const int8_t* obs_base, const int32_t* 
     rt.launches++;
   }
   const int n_conv = 1 + 2 * n->blocks;
-  cudaEventRecord(n->ev_tower[0], rt.stream);
+  cudaEvent_t* evp = n->ev_tower[n->n_forwards % AzNet::kTowerRing];
+  cudaEventRecord(evp[0], rt.stream);
   for (int li = 0; li < n_conv; ++li) aznet_tc_layer(n, rt, li, true, n_rows_dev, max_rows);
-  cudaEventRecord(n->ev_tower[1], rt.stream);
+  cudaEventRecord(evp[1], rt.stream);
+  n->n_forwards++;
   launch_heads<__nv_bfloat16>(rt.stream, (const __nv_bfloat16*)n->act_x, row_list, n_rows_dev, n->hp, g, n->C, tc->split ? 3 * n->C : n->C, tc->split, n->A, n->fc,
                               priors_base, values_base, pri_stride, max_rows);
   rt.launches++;

@@ -508,6 +508,8 @@ def main():
         n_conv = 1 + 2 * nb
         # algorithmic 2*MAC of the tower per leaf, layer by layer: the input layer has 17 input planes, not nf
         tower_flops = 2.0 * hw * 9 * 17 * nf + (n_conv - 1) * 2.0 * hw * 9 * nf * nf
+        # tower_ms = mean over the last 64 ticks of the timed region; leaves per tick = this rank's evaluations of the region / its ticks
+        tower_evals = int(round((c1['evaluations'] - c0['evaluations']) / max(1, a.steps * ticks))) or tower_evals
         achieved = (tower_evals * tower_flops / (tower_ms * 1e-3) / 1e12) if tower_ms > 0 else None
         is_tc = a.precision in ('bf16', 'bf16x3')
         peak = peaks.get('bf16_tflops_sustained') if is_tc else None
@@ -552,8 +554,8 @@ def main():
                          'frac': (achieved / peak) if achieved else None, 'traffic': traffic, 'traffic_unit': 'bytes per launch (ncu dram__bytes_read+write)',
                          'traffic_source': traffic_src,
                          'algorithmic_bytes_per_launch': 2.0 * tower_evals * hw * nf * 2, 'peak_source': peak_src,
-                         'note': f'algorithmic 2*MAC of the {n_conv} tower layers ({tower_flops / 1e6:.1f} MFLOP/leaf: input layer 17 planes, the rest {nf}x{nf}) x {tower_evals} leaves / '
-                                 f'tower time of the last tick ({tower_ms:.3f} ms for the {n_conv} launches, CUDA events on the engine stream)'
+                         'note': f'algorithmic 2*MAC of the {n_conv} tower layers ({tower_flops / 1e6:.1f} MFLOP/leaf: input layer 17 planes, the rest {nf}x{nf}) x {tower_evals} leaves (mean per tick) / '
+                                 f'mean tower time per tick over the last 64 ticks of the timed region ({tower_ms:.3f} ms for the {n_conv} conv launches, CUDA events on the engine stream around them)'
                                  + ('; the split tower issues 3x these MMAs' if a.precision == 'bf16x3' else '')},
             'clocks': clk.summary(),
             'tick_breakdown_ms': dict({k: v / max(1, phase_ticks) for k, v in phase_ms.items()}, ticks=phase_ticks,

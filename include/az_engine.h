@@ -238,8 +238,8 @@ int az_gather_pack(az_engine* e, az_game_record* records, int32_t max_games, int
                    void* d_values, int32_t max_samples, int32_t* n_samples);
 /* The CUDA stream every engine kernel is launched on (bench.py times on it with its own events). */
 int az_stream(az_engine* e, void** cuda_stream);
-/* Device time (ms) of the tower's conv launches in the most recent network call of az_selfplay_tick (CUDA events on the engine
- * stream around the conv layers only: no input / heads kernels), and the number of leaves it evaluated: bench.py's roofline. */
+/* Mean device time (ms) of the tower's conv launches per network call over the most recent (up to 64) calls (CUDA events on the
+ * engine stream around the conv layers only: no input / heads kernels), and the leaves of the last call: bench.py's roofline. */
 int az_last_net_ms(az_engine* e, float* ms, int32_t* n_evals);
 
 /* Per-phase device time of the self-play tick, for the measurement tooling (bench.py `tick_breakdown_ms`): with profiling

@@ -64,4 +64,4 @@ int aznet_debug_layer(AzNet*, AzRt&, int, const float*, const float*, int, float
 }
 int aznet_tc_mode_of(const AzNet*) { return -1; }
 int aznet_padded_filters(const AzNet*) { return 0; }
-float aznet_last_tower_ms(const AzNet*) { return 0.f; }
+float aznet_last_tower_ms(const AzNet*, int* n) { if (n) *n = 0; return 0.f; }
