@@ -135,8 +135,23 @@ static int alloc_check(az_engine* e, const char* where) {
 
 // One engine is bound to one CUDA device, but the calling thread's current device may be anything (another thread of the
 // process, torch.cuda.set_device): every entry point makes the engine's device current before it allocates or launches.
+// The caller's device is put back when the entry point returns (torch keeps its own notion of the current device per thread).
 #ifndef AZ_EMU
-#define AZ_ENTER(e) do { if (e) cudaSetDevice((e)->rt.device); } while (0)
+struct AzDeviceGuard {
+  int prev = -1;
+  explicit AzDeviceGuard(int dev) {
+    if (dev < 0) return;
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != dev) {
+      prev = cur;
+      cudaSetDevice(dev);
+    }
+  }
+  ~AzDeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+#define AZ_ENTER(e) AzDeviceGuard az_device_guard_((e) ? (e)->rt.device : -1)
 #else
 #define AZ_ENTER(e) do { } while (0)
 #endif
@@ -169,6 +184,9 @@ static void build_tables(az_engine* e, double cb, double ci) {
 
 extern "C" int az_create(const az_config* cfg, az_engine** out) {
   if (!cfg || !out) return az_fail(AZ_ERR_BAD_ARG, "az_create: null argument");
+#ifndef AZ_EMU
+  AzDeviceGuard az_device_guard_(cfg->device);  // the engine's device is current while it is built; the caller's comes back afterwards
+#endif
   if (cfg->game != AZ_GAME_GO && cfg->game != AZ_GAME_GOMOKU) return az_fail(AZ_ERR_BAD_ARG, "az_create: unknown game");
   if (cfg->board_size < 3 || cfg->board_size > 19) return az_fail(AZ_ERR_BAD_ARG, "az_create: board_size must be in [3, 19]");
   if (cfg->num_stack < 1 || cfg->num_stack > 8) return az_fail(AZ_ERR_BAD_ARG, "az_create: num_stack must be in [1, 8]");

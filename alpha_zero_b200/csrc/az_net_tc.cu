@@ -33,6 +33,7 @@
 struct AzNetTc {
   CUtensorMap map_in, map_x, map_mid;
   CUtensorMap hmap_in[2], hmap_x[2], hmap_mid[2];  // halo kernel: [0] 256-row box, [1] tail box (AR-256 rows)
+  int pdl = 1;             // AZ_PDL (default 1): conv layers 1.. are launched with programmatic stream serialization
   int split = 0;           // AZ_NET_BF16X3: activation rows [hi | lo | hi] (3 C channels), weights [W_hi | W_hi | W_lo]
   int mode = 0;            // AZ_TC_MODE: 0 = one TMA box per tap, 1/2 = halo tile + row-shifted descriptors (base-offset variants)
   int halo = 0, AR = 0;
@@ -737,6 +738,11 @@ k_conv_tc_x(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   if (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch (AZ_PDL, default on): the next layer's CTAs may be placed as soon as this grid's CTAs leave their SMs, and
+  // this grid's set-up above (barriers, TMEM, cluster handshake, bias) overlapped the previous layer's tail; nothing written by the
+  // previous layer is touched before this point.  Both instructions are no-ops for a launch without the attribute.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ===== TMA producer: sub-tiles (kk, dx) and weight chunks (kk, dx, dy) in the order the MMA warps consume them =====
@@ -1080,6 +1086,8 @@ int aznet_tc_create(AzNet* n, AzRt& rt, std::string& err) {
   cudaDeviceGetAttribute(&tc->num_sms, cudaDevAttrMultiProcessorCount, dev);
   const char* rp = getenv("AZ_TC_RESPF");
   tc->res_l2 = rp ? atoi(rp) : 0;
+  const char* pd = getenv("AZ_PDL");
+  tc->pdl = pd ? atoi(pd) : 1;
   const char* md = getenv("AZ_TC_MODE");
   // 5 = dense-x layout + 2-CTA pairs (default), 6 = dense-x single CTA, 4 = halo tile + 2-CTA pairs, 2 = halo tile single CTA,
   // 0 = one TMA box per tap
@@ -1242,11 +1250,13 @@ int aznet_tc_layer(AzNet* n, AzRt& rt, int li, bool with_res, const int32_t* n_r
       cfg.blockDim = dim3(H_THREADS);
       cfg.dynamicSmemBytes = tc->x_smem;
       cfg.stream = rt.stream;
-      cudaLaunchAttribute at[1];
+      cudaLaunchAttribute at[2];
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[1].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = at;
-      cfg.numAttrs = 1;
+      cfg.numAttrs = (tc->pdl && li > 0) ? 2 : 1;  // layer 0 follows k_net_input, an ordinary launch
       if (tc->split) cudaLaunchKernelEx(&cfg, k_conv_tc_x<true, true>, ma, tc->map_w_half[li], bias, resp, outp, n_rows_dev, X5);
       else cudaLaunchKernelEx(&cfg, k_conv_tc_x<true, false>, ma, tc->map_w_half[li], bias, resp, outp, n_rows_dev, X5);
     }
