@@ -9,6 +9,7 @@ Two ways of playing:
     game, honouring ckpt_event / stop_event / var_ckpt / var_resign_threshold like the reference actor.
 """
 import os
+import queue
 import random
 import time
 from collections import OrderedDict
@@ -260,8 +261,19 @@ def run_selfplay_actor_loop(seed, rank, network, device, data_queue, env, num_si
                                komi=getattr(env, 'komi', ''), date=get_time_stamp())
                 with open(os.path.join(save_sgf_dir, f'actor{rank}_{get_time_stamp(True)}_{played_games}.sgf'), 'w') as f:
                     f.write(sgf)
-            data_queue.put((seq, stats))
+            # a bounded queue (maxsize = num_actors, training_go.py:279) fills up when the learner is busy or has finished: keep
+            # looking at the stop signal instead of blocking in put() for ever
+            while not stop_event.is_set():
+                try:
+                    data_queue.put((seq, stats), timeout=0.5)
+                    break
+                except queue.Full:
+                    continue
 
     logger.debug(f'Actor{rank} received stop signal.')
     writer.close()
     engine.close()
+    # the learner has stopped reading by now: do not let this process wait at exit for its queue feeder thread to push a last,
+    # never-to-be-read game through the pipe (the driver joins the actors, training_go.py:384-388)
+    if hasattr(data_queue, 'cancel_join_thread'):
+        data_queue.cancel_join_thread()
