@@ -8,7 +8,7 @@ Everything else is the reference's own code: flags, process wiring (`spawn`, mp.
 (UniformReplay, compute_losses, SGD, checkpoint writer, resign controller) and the evaluator (its own MCTS + Elo).  The actor
 process is ours: one process driving $AZ_ACTOR_GAMES concurrent games on an engine.
 
-    python tools/run_reference_training_go.py --emu [--out DIR] [training_go flags...]
+    python tools/run_reference_training_go.py --emu [--driver training_gomoku.py] [--out DIR] [driver flags...]
 
 `--emu` makes the engine the HOST EMULATION build (tests/emu/libaz_emu.so: same game / tree / host-ABI code compiled for the
 host, a hash of the observation standing in for the network) — the only way to run this in the build container, which has no GPU;
@@ -29,6 +29,11 @@ def main():
     emu = '--emu' in argv
     if emu:
         argv.remove('--emu')
+    driver = 'training_go.py'
+    if '--driver' in argv:  # training_go.py (default) | training_gomoku.py | training_go_jumbo.py: same wiring, other env / defaults
+        i = argv.index('--driver')
+        driver = argv[i + 1]
+        del argv[i:i + 2]
     out = None
     if '--out' in argv:
         i = argv.index('--out')
@@ -52,17 +57,17 @@ def main():
         '--replay_capacity=20000', '--init_resign_threshold=-1', '--eval_games_dir=/nonexistent', '--save_sgf_interval=5',
         f'--ckpt_dir={out}/ckpt', f'--logs_dir={out}/logs', f'--save_sgf_dir={out}/sgf', '--log_level=DEBUG',
     ]
-    sys.argv = [os.path.join(REF, 'alpha_zero', 'training_go.py')] + defaults + argv
+    sys.argv = [os.path.join(REF, 'alpha_zero', driver)] + defaults + argv
     # go_engine.py reads BOARD_SIZE when it is first imported (go_engine.py:31); training_go.py sets it from its flag before ITS
     # imports (training_go.py:204-208), and so must whoever imports the reference earlier
     board = [a.split('=')[1] for a in sys.argv if a.startswith('--board_size=')]
-    os.environ['BOARD_SIZE'] = board[-1] if board else '9'
+    os.environ['BOARD_SIZE'] = board[-1] if board else ('19' if 'jumbo' in driver else '9')
     import gym  # noqa: F401  (the shim; installs the emulation binding when AZ_TEST_EMU_BINDING is set)
     import alpha_zero.core.pipeline as ref_pipeline
     from alpha_zero_b200.pipeline import run_selfplay_actor_loop
 
     ref_pipeline.run_selfplay_actor_loop = run_selfplay_actor_loop  # THE import swap
-    print(f'[import swap] training_go.py will import run_selfplay_actor_loop from {run_selfplay_actor_loop.__module__}; output in {out}', flush=True)
+    print(f'[import swap] {driver} will import run_selfplay_actor_loop from {run_selfplay_actor_loop.__module__}; output in {out}', flush=True)
     runpy.run_path(sys.argv[0], run_name='__main__')
 
 
